@@ -1,0 +1,195 @@
+/*
+ * lfe.h -- C ABI of liblfe.so: B200 (sm_100a) kernels for the leanfe estimation hot path.
+ *
+ * This is the drop-in boundary.  The reference (jorgenhost/leanfe) has no FFI of its own: its
+ * hot path is Polars expressions + NumPy calls inside python/leanfe/polars_impl.py,
+ * python/leanfe/std_errors.py and python/leanfe/compress.py.  Each entry point below replaces the
+ * reference code cited beside it (paths relative to the reference repo root) and is what a
+ * maintainer would bind with ctypes from those call sites.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (LFE_ERR_*); lfe_last_error() gives the
+ *     thread-local message of the last failing call.
+ *   - array arguments are DEVICE pointers owned by the caller unless marked [host]; the library
+ *     never frees or keeps caller memory.  Scratch is stream-ordered (cudaMallocAsync on `stream`)
+ *     and released before the call returns.
+ *   - columns are struct-of-arrays: one contiguous double array per column, one int32 array per
+ *     group-code column.  Row counts must be < 2^31.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous except where a [host] scalar is returned (those synchronise `stream`).
+ *   - a "pointer array" argument (e.g. double* const* cols) is a HOST array of device pointers.
+ */
+#ifndef LFE_H
+#define LFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lfe_ctx* lfe_handle;
+
+enum {
+  LFE_OK = 0,
+  LFE_ERR_ARG = -1,       /* bad argument */
+  LFE_ERR_CUDA = -2,      /* CUDA runtime error */
+  LFE_ERR_CAPACITY = -3,  /* caller buffer too small (e.g. uniques_cap) */
+  LFE_ERR_UNSUPPORTED = -4,
+  LFE_ERR_NCCL = -5
+};
+
+/* key dtypes for lfe_factorize / lfe_compress */
+enum { LFE_I32 = 0, LFE_I64 = 1, LFE_U32 = 2, LFE_U64 = 3, LFE_F64 = 4, LFE_U8 = 5 };
+/* code order: 0 = rank among ascending sorted uniques (== np.unique(..., return_inverse=True)),
+ *             1 = first-appearance rank (== pandas.factorize)                                    */
+enum { LFE_ORDER_SORTED = 0, LFE_ORDER_FIRST = 1 };
+/* vcov kinds (python/leanfe/std_errors.py:83-176) */
+enum { LFE_VCOV_IID = 0, LFE_VCOV_HC1 = 1, LFE_VCOV_CLUSTER = 2 };
+
+#define LFE_MAX_FE 8
+#define LFE_MAX_CLUSTER_WAYS 4
+#define LFE_N_TIMERS 16
+
+int lfe_version(void);
+const char* lfe_last_error(void);
+
+/* one handle per device; not thread-safe per handle */
+int lfe_create(int device, lfe_handle* out);
+int lfe_destroy(lfe_handle h);
+
+/* Per-phase CUDA-event timers (ms, accumulated since the last reset); enabling costs two
+ * cudaEventRecord per phase.  lfe_get_timers synchronises the recorded events.
+ * slots: 0 factorize, 1 counts/singletons, 2 compact, 3 sort, 4 gather, 5 demean-setup (CSR + S0),
+ *        6 demean sweeps, 7 convergence checks, 8 demean apply, 9 gram, 10 solve, 11 resid/vcov,
+ *        12 compress, 13 collectives.  lfe_get_counters: kernel launches since reset ([0]), sweep
+ *        projection launches ([1]).                                                             */
+int lfe_set_profiling(lfe_handle h, int enabled);
+int lfe_reset_timers(lfe_handle h);
+int lfe_get_timers(lfe_handle h, double* ms_out /*[host] LFE_N_TIMERS*/);
+int lfe_get_counters(lfe_handle h, int64_t* out /*[host] 4*/);
+
+/* ---- (1) group codes -------------------------------------------------------------------------
+ * Replaces: `cast(pl.Categorical).to_physical()` polars_impl.py:118-139 (order 1), the implicit
+ * hashing of every `.over(fe)` / `group_by` (polars_impl.py:434,479,503; std_errors.py:329,408),
+ * `np.unique(..., return_inverse=True)` compress.py:585-590,842 (order 0), and `n_unique`
+ * polars_impl.py:371-373.  Float keys are canonicalised (-0.0 -> +0.0, all NaN equal).
+ * uniques_out (nullable) receives the distinct keys in code order, dtype = key dtype; if
+ * n_groups > uniques_cap the call fails with LFE_ERR_CAPACITY (n_groups_out is still set).       */
+int lfe_factorize(lfe_handle h, const void* keys, int key_dtype, int64_t n, int order,
+                  int32_t* codes_out, int64_t* n_groups_out /*[host]*/,
+                  void* uniques_out, int64_t uniques_cap, void* stream);
+
+/* counts_out[g] = #rows with codes == g  (int32, length n_groups) */
+int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_groups,
+                     int32_t* counts_out, void* stream);
+
+/* ---- singleton filter -------------------------------------------------------------------------
+ * Replaces: `lf.filter(all_horizontal(len().over(fe) > 1))` polars_impl.py:478-482 (434-435).
+ * keep_out[i] = 1 iff every FE's group of row i has more than one row; ONE pass on the input.
+ * fe_dims_out[j] (nullable) = number of distinct codes of FE j among kept rows (:531-534).       */
+int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
+                       int64_t n, uint8_t* keep_out, int64_t* n_keep_out /*[host]*/,
+                       int64_t* fe_dims_out /*[host] F*/, void* stream);
+
+/* stable compaction of C double columns and K int32 columns by keep[]; outputs have n_keep rows */
+int lfe_compact(lfe_handle h, const uint8_t* keep, int64_t n,
+                const double* const* f64_in, double* const* f64_out, int C,
+                const int32_t* const* i32_in, int32_t* const* i32_out, int K, void* stream);
+
+/* ---- row ordering -----------------------------------------------------------------------------
+ * Stable argsort of rows by a dense code column (the highest-cardinality FE: its groups become
+ * contiguous segments, and it is the multi-GPU shard key).  perm_out[p] = source row of sorted
+ * position p.  already_sorted_out [host] = 1 when the input was already non-decreasing (perm is
+ * then the identity and the caller may skip the gathers).                                        */
+int lfe_sort_rows(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_groups,
+                  int32_t* perm_out, int* already_sorted_out /*[host]*/, void* stream);
+int lfe_gather(lfe_handle h, const int32_t* perm, int64_t n,
+               const double* const* f64_in, double* const* f64_out, int C,
+               const int32_t* const* i32_in, int32_t* const* i32_out, int K, void* stream);
+
+/* ---- (2) FWL alternating projections ----------------------------------------------------------
+ * Replaces: the demeaning loop polars_impl.py:490-526 (and the single-FE within transform
+ * :438-457 with max_iter = 1, min_iter > 1).  cols[0] is y.  In place: on return every column
+ * holds c - sum_j alpha_j[code_j].  fe_order = FE indices in sweep order (ascending pre-drop
+ * cardinality, :485).  From sweep `min_iter` (reference: 3) on, after each full sweep
+ * max_fe max_g |mean_g(y)| (UNWEIGHTED, :511-521) is compared with tol.  weights nullable
+ * (weighted mean = sum(w c)/sum(w), :492-500).  n_groups[j] bounds codes[j]; empty groups are
+ * allowed.  With a communicator attached (lfe_comm_init) rows are assumed sharded so that FE
+ * `local_fe` (>= 0) has all rows of each of its groups on one rank; all other FE tables are
+ * all-reduced once per projection.                                                              */
+#define LFE_DEMEAN_STRICT_CHECK 1 /* flags bit: stop on max |weighted group mean| over ALL columns < tol
+                                    (true fixed point; used for the YOCO solve) instead of the reference test */
+int lfe_demean(lfe_handle h, double* const* cols, int C, const int32_t* const* codes,
+               const int64_t* n_groups, const int* fe_order, int F, int64_t n,
+               const double* weights, double tol, int max_iter, int min_iter, int local_fe, int flags,
+               int* iterations_out /*[host]*/, double* max_mean_out /*[host]*/,
+               int* converged_out /*[host]*/, void* stream);
+
+/* ---- (4) Gram + solve --------------------------------------------------------------------------
+ * Replaces: X = [1 | X~], X'X, X'y  polars_impl.py:166-209 (weighted: sqrt(w) scaling :201-206).
+ * Z = [1 | cols[0] .. cols[C-1]] when add_intercept else [cols]; gram_out (device, P x P row-major,
+ * P = C + add_intercept) = Z' diag(w) Z.  All-reduced over the communicator if attached.         */
+int lfe_gram(lfe_handle h, const double* const* cols, int C, int64_t n, const double* weights,
+             int add_intercept, double* gram_out, void* stream);
+
+/* Replaces: np.linalg.cholesky + two triangular solves for beta and (X'X)^-1, with the
+ * LinAlgError -> np.linalg.solve / inv fallback, polars_impl.py:212-220.  A (p x p), b (p),
+ * beta_out (p), Ainv_out (p x p) are device pointers; p <= 512.                                  */
+int lfe_solve_spd(lfe_handle h, const double* A, const double* b, int p, double* beta_out,
+                  double* Ainv_out, int* used_fallback_out /*[host], nullable*/, void* stream);
+
+/* ---- (5) residuals + sandwich vcov ------------------------------------------------------------
+ * Replaces: resid / R^2 polars_impl.py:229, 281-283 and compute_standard_errors_polars
+ * std_errors.py:183-441.  cols[0] = y~, cols[1..k] = x~ (demeaned).  beta_full (device, k+1:
+ * intercept first), Binv (device k x k = (X'X)^-1[1:,1:]).  cl_codes: W cluster code columns
+ * (W = 0 unless vcov_kind == CLUSTER; W > 1 = Cameron-Gelbach-Miller multiway, :354-441).
+ * Outputs (device): se_out (k), vcov_out (k x k, nullable), stats_out (4: rss, tss, sum_w_r2, 0).
+ * n_clusters_out [host] (W).  resid_out nullable (device, n).                                    */
+int lfe_resid_vcov(lfe_handle h, const double* const* cols, int k, int64_t n,
+                   const double* beta_full, const double* Binv, int vcov_kind,
+                   const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W,
+                   const double* weights, int ssc, int64_t n_obs, int64_t df_resid,
+                   double* se_out, double* vcov_out, double* stats_out, double* resid_out,
+                   int64_t* n_clusters_out /*[host]*/, void* stream);
+
+/* ---- (3) YOCO compression ---------------------------------------------------------------------
+ * Replaces: lf.group_by(x_cols + fe_cols + cluster_cols).agg(len, sum y, sum y^2)
+ * compress.py:325-350 and the distinct count of estimate_compression_ratio compress.py:249-250.
+ * key_codes: K int32 code columns (from lfe_factorize, order 0) with cardinalities n_groups[K].
+ * Groups are emitted in ascending lexicographic order of the code tuples.  Outputs have capacity
+ * out_cap rows: key_codes_out[K] (int32), n_out (sum of weights, or count), cnt_out (int32 raw
+ * count), sum_y_out, sum_y_sq_out.  y may be NULL (count-distinct only; stats outputs NULL).     */
+int lfe_compress(lfe_handle h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
+                 const double* y, const double* weights, int64_t n, int64_t out_cap,
+                 int32_t* const* key_codes_out, double* n_out, int32_t* cnt_out,
+                 double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out /*[host]*/,
+                 void* stream);
+
+/* ---- YOCO standard errors --------------------------------------------------------------------
+ * Replaces: compute_rss_grouped compress.py:754-810, e0_g compress.py:1124-1137 and compute_se_compress
+ * compress.py:854-1042 -- without the FE dummy matrix of compress.py:503-619: cols[0] = W-weighted
+ * FE-demeaned group means y~, cols[1..k] = demeaned regressors x~ (compressed rows, G of them);
+ * beta (device, k) and Binv (device, k x k) = (X~'WX~)^-1; nn / sum_y / sum_y_sq = the sufficient
+ * statistics of lfe_compress.  cl_codes index compressed rows.  rss_out (device scalar, nullable). */
+int lfe_yoco_vcov(lfe_handle h, const double* const* cols, int k, int64_t n_compressed,
+                  const double* beta, const double* Binv, const double* nn, const double* sum_y,
+                  const double* sum_y_sq, int vcov_kind, const int32_t* const* cl_codes,
+                  const int64_t* n_cl_groups, int W, int ssc, int64_t n_obs, int64_t df_resid,
+                  double* se_out, double* vcov_out, double* rss_out,
+                  int64_t* n_clusters_out /*[host]*/, void* stream);
+
+/* ---- multi-GPU ----------------------------------------------------------------------------------
+ * One process per GPU.  Rank 0 calls lfe_comm_unique_id, the 128 bytes are broadcast by the host
+ * (torch.distributed), every rank calls lfe_comm_init.  NCCL is dlopen'ed at run time.          */
+int lfe_comm_unique_id(void* id_out /*[host] 128 bytes*/);
+int lfe_comm_init(lfe_handle h, const void* id /*[host] 128 bytes*/, int rank, int world);
+int lfe_comm_destroy(lfe_handle h);
+/* sum all-reduce of a device double buffer over the attached communicator (no-op if none) */
+int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFE_H */

@@ -1,0 +1,309 @@
+"""``leanfe()`` -- the reference's public entry point, backed by the B200 library.
+
+Signature, defaults, strategy selection and error behaviour follow the reference
+(python/leanfe/leanfe.py:14-184 -> python/leanfe/polars_impl.py:287-579).  Everything per-row runs in
+liblfe.so (``include/lfe.h``); this module only orchestrates.  Deviations (all listed in DESIGN.md):
+'hc1' and 'HC1' are both accepted, expanded factor/interaction columns are kept (reference bug), dummy
+names use the original labels, IV is not implemented, ``compression_ratio`` is only computed when
+the strategy rule actually needs it.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from .engine import Engine, get_engine
+from .formula import parse_formula
+from .frontend import Frame, KeyColumn, resolve_reference, to_device_f64, to_device_key
+from .result import LeanFEResult
+from .strategy import MAX_FE_LEVELS, determine_strategy
+
+
+class InvalidVcov(AssertionError, ValueError):
+    """The reference asserts on the vcov name (polars_impl.py:158) and raises ValueError later
+    (std_errors.py:176); this is both."""
+
+
+_VCOV = {"iid": capi.VCOV_IID, "hc1": capi.VCOV_HC1, "cluster": capi.VCOV_CLUSTER}
+
+
+def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strategy="auto", weights=None,
+           demean_tol=1e-6, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None,
+           backend="polars", con=None, device=None, profile=False) -> LeanFEResult:
+    """Fast fixed-effects regression; drop-in for ``leanfe.leanfe`` with the compute on a B200.
+
+    ``backend`` accepts "polars" (the backend this package replaces), "b200" or "cuda"; "duckdb" is a
+    different engine of the reference and is out of scope.
+    """
+    if backend in ("polars", "b200", "cuda"):
+        if data is None:
+            raise ValueError(f"A dataset must be provided when using backend = {backend}.")
+        return leanfe_b200(data=data, y_col=y_col, x_cols=x_cols, fe_cols=fe_cols, formula=formula,
+                           strategy=strategy, weights=weights, demean_tol=demean_tol, max_iter=max_iter, vcov=vcov,
+                           cluster_cols=cluster_cols, ssc=ssc, sample_frac=sample_frac, device=device,
+                           profile=profile)
+    if backend == "duckdb":
+        raise ValueError("backend='duckdb' is not provided by leanfe_b200 (out of scope: it replaces the Polars "
+                         "backend's compute); use backend='polars'")
+    raise ValueError(f"backend must be 'polars' or 'duckdb', got '{backend}'")
+
+
+def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, formula=None, strategy="auto",
+                weights=None, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None, device=None,
+                profile=False) -> LeanFEResult:
+    """Counterpart of ``leanfe_polars`` (polars_impl.py:287-301) on the device."""
+    t_start = time.perf_counter()
+    if formula is not None:
+        y_col, x_cols, fe_cols, factor_vars, interactions, instruments = parse_formula(formula)
+    elif y_col is None or x_cols is None or fe_cols is None:
+        raise ValueError("Must provide either 'formula' or (y_col, x_cols, fe_cols)")
+    else:
+        factor_vars, interactions, instruments = [], [], []
+    if instruments:
+        raise NotImplementedError("IV/2SLS is outside the scope of leanfe_b200 (SURVEY 8f.4)")
+    if not isinstance(vcov, str) or vcov.lower() not in _VCOV:
+        raise InvalidVcov(f"Invalid vcov method: {vcov}")
+    vkind = _VCOV[vcov.lower()]
+    cluster_cols = list(cluster_cols) if cluster_cols else None
+    if vkind == capi.VCOV_CLUSTER and not cluster_cols:
+        raise ValueError("cluster_cols required for vcov='cluster'")
+    x_cols = list(x_cols)
+    fe_cols = list(fe_cols) if fe_cols is not None else []
+    if strategy not in ("auto", "compress", "alt_proj", "demean", "ols"):
+        raise ValueError(f"Unknown strategy: {strategy}")
+
+    # needed columns (polars_impl.py:325-339)
+    needed = [y_col] + x_cols + fe_cols
+    for var, _ in factor_vars:
+        if var not in needed:
+            needed.append(var)
+    for var, factor, _ in interactions:
+        for c in (var, factor):
+            if c not in needed:
+                needed.append(c)
+    if cluster_cols:
+        needed += [c for c in cluster_cols if c not in needed]
+    if weights is not None and weights not in needed:
+        needed.append(weights)
+
+    eng = get_engine(device)
+    if profile:
+        eng.set_profiling(True)
+        eng.reset_timers()
+    frame = Frame(data, needed)
+    numeric: dict[str, torch.Tensor] = {}
+    keys: dict[str, KeyColumn] = {}
+
+    def num(name):
+        if name not in numeric:
+            numeric[name] = to_device_f64(eng, frame.column(name))
+        return numeric[name]
+
+    def key(name, labels=False):
+        if name not in keys or (labels and keys[name].labels is None):
+            keys[name] = to_device_key(eng, frame.column(name), want_labels=labels)
+        return keys[name]
+
+    y = num(y_col)
+    X = [num(c) for c in x_cols]
+    w = num(weights) if weights is not None else None
+
+    # interactions then factors (polars_impl.py:350-365); labels come from the original values
+    for var, factor, ref in interactions:
+        kc = key(factor, labels=True)
+        ref_cat = resolve_reference(kc.labels, ref, factor)
+        base = num(var)
+        for j, cat in enumerate(kc.labels):
+            if cat == ref_cat:
+                continue
+            X.append(base * (kc.codes == j))
+            x_cols.append(f"{var}_{cat}")
+    for var, ref in factor_vars:
+        kc = key(var, labels=True)
+        ref_cat = resolve_reference(kc.labels, ref, var)
+        for j, cat in enumerate(kc.labels):
+            if cat == ref_cat:
+                continue
+            X.append((kc.codes == j).to(torch.float64))
+            x_cols.append(f"{var}_{cat}")
+
+    fe_keys = [key(c) for c in fe_cols]
+    cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
+    n0 = y.numel()
+
+    if sample_frac is not None:
+        # the reference samples with Polars' RNG (seed 42, polars_impl.py:359-360); not reproducible without
+        # Polars, so sampled fits are parity-unpinned
+        g = torch.Generator(device=eng.device)
+        g.manual_seed(42)
+        m = int(n0 * sample_frac)
+        idx = torch.randperm(n0, generator=g, device=eng.device)[:m].sort().values
+        y, X = y[idx].contiguous(), [c[idx].contiguous() for c in X]
+        w = w[idx].contiguous() if w is not None else None
+        fe_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in fe_keys]
+        cl_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in cl_keys]
+        n0 = m
+
+    fe_card = {c: k_.n_groups for c, k_ in zip(fe_cols, fe_keys)}
+    est_ratio = None
+    if strategy == "auto":
+        def ratio():
+            # distinct rows over set(x_cols + fe_cols) / N   (compress.py:232-253)
+            names = list(dict.fromkeys(x_cols + fe_cols))
+            kcs = []
+            for nm in names:
+                if nm in fe_cols:
+                    kcs.append(fe_keys[fe_cols.index(nm)])
+                else:
+                    c_, G_, _ = eng.factorize(X[x_cols.index(nm)])
+                    kcs.append(KeyColumn(c_, G_))
+            if not kcs:
+                return 1.0
+            r = eng.compress([k_.codes for k_ in kcs], [k_.n_groups for k_ in kcs], None, count_only=True)
+            return r["n_compressed"] / max(n0, 1)
+
+        if not fe_cols:
+            est_ratio = ratio()
+            strategy = "ols" if est_ratio >= 0.8 else "compress"
+        elif len(fe_cols) == 1:
+            strategy = "demean"
+        else:
+            # rules 1/2 of determine_strategy do not need the ratio; compute it only for the cost model
+            total, mx = sum(fe_card.values()), max(fe_card.values())
+            if mx > MAX_FE_LEVELS or total > 2 * MAX_FE_LEVELS:
+                strategy = "alt_proj"
+            else:
+                est_ratio = ratio()
+                strategy = determine_strategy(vcov, False, fe_card, MAX_FE_LEVELS, n0, len(x_cols), est_ratio)
+
+    if strategy == "compress":
+        res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
+        res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
+    else:
+        res = _fit_fwl(eng, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, demean_tol,
+                       max_iter, formula, est_ratio)
+    if profile:
+        torch.cuda.synchronize(eng.device)
+        res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
+        eng.set_profiling(False)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
+             formula, est_ratio) -> LeanFEResult:
+    """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression."""
+    k = len(X)
+    F = len(fe_keys)
+    if strategy == "demean" and F != 1:
+        raise ValueError("Strategy 'demean' requires exactly one FE column.")
+    if strategy == "alt_proj" and F == 0:
+        raise ValueError("Strategy 'alt_proj' requires FE-cols. Use strategy='ols' instead for OLS without FE.")
+    cols = [y] + list(X)
+    cl_codes = [c.codes for c in cl_keys]
+    iterations, converged, fe_dims, absorbed = 0, None, None, 0
+    if strategy != "ols":
+        codes = [f.codes for f in fe_keys]
+        Gs = [f.n_groups for f in fe_keys]
+        # singleton filter: one pass, all FEs (polars_impl.py:478-482)
+        keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs)
+        owned = False
+        if n_keep < y.numel():
+            f_in = cols + ([w] if w is not None else [])
+            f_out, i_out = eng.compact(keep, n_keep, f_in, codes + cl_codes)
+            cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
+            codes, cl_codes = i_out[:F], i_out[F:]
+            owned = True
+        # order rows by the highest-cardinality FE: its groups become contiguous segments
+        big = max(range(F), key=lambda j: Gs[j])
+        perm, is_sorted = eng.sort_rows(codes[big], Gs[big])
+        if not is_sorted:
+            f_in = cols + ([w] if w is not None else [])
+            f_out, i_out = eng.gather(perm, f_in, codes + cl_codes)
+            cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
+            codes, cl_codes = i_out[:F], i_out[F:]
+            owned = True
+        del perm
+        if not owned:
+            cols = [c.clone() for c in cols]          # lfe_demean works in place; never touch caller data
+        order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
+        if strategy == "demean":
+            iterations, _, _ = eng.demean(cols, codes, Gs, order, w, tol, 1, 2)
+            iterations, converged = 1, True
+            absorbed = fe_dims[0] - 1
+        else:
+            iterations, _, converged = eng.demean(cols, codes, Gs, order, w, tol, max_iter, 3)
+            absorbed = sum(fe_dims) - F
+    n_obs = cols[0].numel()
+    # regression on [1 | X~] (polars_impl.py:166-226)
+    gram = eng.gram(cols[1:] + [cols[0]], w, add_intercept=True)       # order: 1, x.., y
+    p = k + 1
+    XtX, Xty = gram[:p, :p].contiguous(), gram[:p, p].contiguous()
+    beta_full, XtX_inv, _ = eng.solve_spd(XtX, Xty)
+    df_resid = n_obs - p - absorbed
+    B = XtX_inv[1:, 1:].contiguous()
+    out = eng.resid_vcov(cols, beta_full, B, vkind, cl_codes, [c.n_groups for c in cl_keys], w, ssc, n_obs, df_resid)
+    host = torch.cat([beta_full, out["se"], out["stats"]]).cpu().numpy()
+    beta, se, (rss, tss) = host[1:p], host[p:p + k], host[p + k:p + k + 2]
+    n_clusters = None
+    if vkind == capi.VCOV_CLUSTER:
+        n_clusters = out["n_clusters"][0] if len(cl_keys) == 1 else tuple(out["n_clusters"])
+    r2 = float(1 - rss / tss) if tss > 0 else None
+    return LeanFEResult(coefs=dict(zip(x_cols, beta.tolist())), std_errors=dict(zip(x_cols, se.tolist())), n_obs=n_obs,
+                        iterations=iterations, vcov_type=vcov, is_iv=False, n_instruments=None, n_clusters=n_clusters,
+                        df_resid=df_resid, formula=formula, fe_cols=fe_cols, fe_dims=fe_dims, r_squared=r2,
+                        compression_ratio=est_ratio, rss=float(rss), tss=float(tss), strategy=strategy,
+                        converged=converged)
+
+
+def _fit_compress(eng: Engine, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n_obs):
+    """YOCO (compress.py:1049-1174): device group-by, then FWL on the compressed rows."""
+    k, F = len(X), len(fe_keys)
+    if k == 0:
+        raise ValueError("strategy='compress' needs at least one regressor")
+    group_names = x_cols + fe_cols
+    xk = []
+    for c in X:
+        codes, G, uniq = eng.factorize(c, want_uniques=True, uniques_cap=1 << 20)
+        xk.append((codes, G, uniq))
+    kc = [(c, G) for c, G, _ in xk] + [(f.codes, f.n_groups) for f in fe_keys]
+    cl_idx = []
+    for name, ck in zip(cluster_cols or [], cl_keys):
+        if name in group_names:
+            cl_idx.append(group_names.index(name))
+        else:
+            group_names = group_names + [name]
+            kc.append((ck.codes, ck.n_groups))
+            cl_idx.append(len(kc) - 1)
+    comp = eng.compress([c for c, _ in kc], [g for _, g in kc], y, w)
+    G = comp["n_compressed"]
+    kout = comp["key_codes"]
+    # regressor values of each compressed row = uniques[code]; group means; weights n_g
+    Xg = [xk[j][2].index_select(0, kout[j].long()).contiguous() for j in range(k)]
+    nn, sy, syy = comp["n"], comp["sum_y"], comp["sum_y_sq"]
+    cols = [(sy / nn).contiguous()] + Xg
+    fe_codes = [kout[k + j] for j in range(F)]
+    fe_G = [f.n_groups for f in fe_keys]
+    fe_dims = tuple(fe_G) if F else None
+    # no FE: the intercept alone is absorbed, i.e. one "fixed effect" with a single level
+    dm_codes = fe_codes if F else [torch.zeros(G, dtype=torch.int32, device=eng.device)]
+    dm_G = fe_G if F else [1]
+    scale = float(torch.max(torch.abs(cols[0])).item()) + 1.0
+    order = sorted(range(len(dm_G)), key=lambda j: dm_G[j])
+    eng.demean(cols, dm_codes, dm_G, order, nn, 1e-14 * scale, 20000, 1, strict_check=True)
+    gram = eng.gram(cols[1:] + [cols[0]], nn, add_intercept=False)
+    beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
+    p = 1 + k + sum(g - 1 for g in fe_G)
+    df_resid = n_obs - p
+    out = eng.yoco_vcov(cols, beta, B, nn, sy, syy, vkind, [kout[i] for i in cl_idx], [kc[i][1] for i in cl_idx],
+                        ssc, n_obs, df_resid)
+    host = torch.cat([beta, out["se"], out["rss"]]).cpu().numpy()
+    n_clusters = None
+    if vkind == capi.VCOV_CLUSTER:
+        n_clusters = out["n_clusters"][0] if len(cl_idx) == 1 else tuple(out["n_clusters"])
+    return LeanFEResult(coefs=dict(zip(x_cols, host[:k].tolist())), std_errors=dict(zip(x_cols, host[k:2 * k].tolist())),
+                        n_compressed=G, n_obs=n_obs, vcov_type=vcov, df_resid=df_resid, rss=float(host[2 * k]),
+                        n_clusters=n_clusters, fe_dims=fe_dims, strategy="compress", iterations=0)

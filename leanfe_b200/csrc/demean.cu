@@ -1,0 +1,453 @@
+// demean.cu -- FWL alternating projections (reference: python/leanfe/polars_impl.py:490-526).
+//
+// B200 design.  The reference rewrites all C = 1+k columns once per FE per sweep
+// (c <- c - mean_g(c)), i.e. N*F*(16C+8) bytes per sweep.  Here the iteration runs in
+// FE-coefficient space: the columns stay untouched and each FE j keeps a table alpha_j[G_j x C];
+// the current residual of row i is c_i - sum_j alpha_j[code_j(i)].  Projecting on FE j is then
+//
+//     alpha_j[g] <- ( S0_j[g] - sum_{i in g} w_i * sum_{k != j} alpha_k[code_k(i)] ) / n_j[g]
+//
+// with S0_j[g] = sum_{i in g} w_i c_i computed once.  In exact arithmetic this is the reference's
+// Gauss-Seidel sweep (same FE order, same iterates); per sweep it reads only the int32 code columns
+// (in FE-j-sorted order, built once with a radix argsort) and gathers rows of the other FEs' tables
+// (L1/L2-resident for low-cardinality FEs) -- no column traffic and no floating-point scatter.
+// Because every FE's rows are visited in sorted order the group sums are segmented reductions:
+// thread-local run compression, a warp-shuffle segmented scan, and one RED.ADD.F64 per (warp, group)
+// for groups that straddle warps.  After convergence one streaming pass applies the tables to the
+// columns in place.
+#include "common.cuh"
+#include "segreduce.cuh"
+
+void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);  // api.cu
+
+// acc[key][acc_col0 + c] += w * sum_k alpha_k[code_k][col0 + c]    over the FE-sorted entry list
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(PJ_T) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
+                                               const double* __restrict__ w, int64_t n, int ldc, int col0,
+                                               double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes) {
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    int k[PJ_I];
+    load4_i32(key, base, n, vec_codes, k);
+    double v[PJ_I][NC];
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[e][c] = 0.0;
+    for (int o = 0; o < oth.n; ++o) {
+      int oc[PJ_I];
+      load4_i32(oth.code[o], base, n, vec_codes, oc);
+      const double* __restrict__ tab = oth.alpha[o] + col0;
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e) {
+        if (oc[e] >= 0) {
+          const double* row = tab + (size_t)oc[e] * ldc;
+          if (vec2) {
+#pragma unroll
+            for (int c = 0; c < NC / 2; ++c) {
+              double2 t = __ldg(reinterpret_cast<const double2*>(row) + c);
+              v[e][2 * c] += t.x;
+              v[e][2 * c + 1] += t.y;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[e][c] += __ldg(row + c);
+          }
+        }
+      }
+    }
+    if (WEIGHTED) {
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e) {
+        double we = (base + e < n) ? __ldcs(w + base + e) : 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[e][c] *= we;
+      }
+    }
+    segmented_flush<NC>(k, v, acc, ld_acc, acc_col0);
+  }
+}
+
+// acc[key][acc_col0 + c] += w * col_c[perm ? perm[e] : e]     (S0 tables; also sum of weights with NC=1)
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(PJ_T) k_segsum(const int32_t* __restrict__ key, ColPtrs cols,
+                                                 const uint32_t* __restrict__ perm, const double* __restrict__ w,
+                                                 int64_t n, double* __restrict__ acc, int ld_acc, int acc_col0,
+                                                 bool vec_codes) {
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    int k[PJ_I];
+    load4_i32(key, base, n, vec_codes, k);
+    double v[PJ_I][NC];
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e) {
+      bool valid = base + e < n;
+      int64_t src = valid ? (perm ? (int64_t)__ldcs(perm + base + e) : base + e) : 0;
+      double we = 1.0;
+      if (WEIGHTED) we = valid ? __ldcs(w + base + e) : 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double x = valid ? (perm ? __ldg(cols.col[c] + src) : __ldcs(cols.col[c] + src)) : 0.0;
+        v[e][c] = WEIGHTED ? x * we : x;
+      }
+    }
+    segmented_flush<NC>(k, v, acc, ld_acc, acc_col0);
+  }
+}
+
+// alpha <- (S0 - acc) / nsum ; acc <- 0
+// delta_max (nullable): max |alpha_new - alpha_old| = largest weighted group mean of the residual just removed
+__global__ void __launch_bounds__(256) k_finalize(double* __restrict__ alpha, double* __restrict__ acc,
+                                                  const double* __restrict__ S0, const double* __restrict__ nsum,
+                                                  int64_t G, int C, double* __restrict__ delta_max) {
+  const int64_t tot = G * C;
+  double m = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    double nn = nsum[i / C];
+    double a = nn > 0.0 ? (S0[i] - acc[i]) / nn : 0.0;
+    if (delta_max) m = fmax(m, fabs(a - alpha[i]));
+    alpha[i] = a;
+    acc[i] = 0.0;
+  }
+  if (delta_max) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_nonneg(delta_max, m);
+  }
+}
+
+// max_g | (S0u[g] - acc[g]) / cnt[g] - alpha[g][0] |   (polars_impl.py:511-521: y only, unweighted)
+__global__ void __launch_bounds__(256) k_check(const double* __restrict__ alpha, double* __restrict__ acc,
+                                               const double* __restrict__ S0u, int ld_s0,
+                                               const double* __restrict__ cnt, int64_t G, int C,
+                                               double* __restrict__ out_max) {
+  double m = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x) {
+    double nn = cnt[g];
+    if (nn > 0.0) {
+      double mean = (S0u[g * ld_s0] - acc[g]) / nn - alpha[g * C];
+      m = fmax(m, fabs(mean));
+    }
+    acc[g] = 0.0;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_nonneg(out_max, m);
+}
+
+__global__ void __launch_bounds__(256) k_u32_to_f64(const uint32_t* __restrict__ in, int64_t n,
+                                                    double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];
+}
+
+// cols[c][i] -= sum_j alpha_j[code_j[i]][col0 + c]
+struct ApplyTabs {
+  const int32_t* code[LFE_MAX_FE];
+  const double* alpha[LFE_MAX_FE];
+  int n;
+};
+template <int NC>
+__global__ void __launch_bounds__(256) k_apply(MutColPtrs cols, ApplyTabs T, int64_t n, int ldc, int col0) {
+  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double s[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s[c] = 0.0;
+    for (int j = 0; j < T.n; ++j) {
+      const double* row = T.alpha[j] + (size_t)__ldcs(T.code[j] + i) * ldc + col0;
+      if (vec2) {
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) {
+          double2 t = __ldg(reinterpret_cast<const double2*>(row) + c);
+          s[2 * c] += t.x;
+          s[2 * c + 1] += t.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s[c] += __ldg(row + c);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double x = __ldcs(cols.col[c] + i);
+      __stcs(cols.col[c] + i, x - s[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct FEState {
+  int64_t G = 0;
+  bool identity = false;
+  DevBuf<uint32_t> perm;
+  DevBuf<int32_t> key_buf;
+  const int32_t* key = nullptr;
+  DevBuf<int32_t> oth_buf[LFE_MAX_FE];
+  const int32_t* oth[LFE_MAX_FE] = {nullptr};
+  DevBuf<double> w_buf;
+  const double* w = nullptr;
+  DevBuf<double> alpha, S0, acc, nsum, cnt_buf, S0u_buf, acc_chk;
+  const double* cnt = nullptr;  // unweighted counts
+  const double* S0u = nullptr;  // unweighted y sums
+  int ld_s0u = 1;
+};
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <bool WEIGHTED>
+static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers& oth, int64_t n, int ldc, int col0,
+                        double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
+  int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  int blocks = launch_blocks(h, nchunk, 8);
+  bool vec = aligned16(st.key);
+  for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
+#define PJ_CASE(NC_)                                                                                             \
+  case NC_:                                                                                                      \
+    k_proj<NC_, WEIGHTED><<<blocks, PJ_T, 0, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc, acc_col0, vec); \
+    break;
+  switch (nc) {
+    PJ_CASE(1) PJ_CASE(2) PJ_CASE(3) PJ_CASE(4) PJ_CASE(5) PJ_CASE(6) PJ_CASE(7) PJ_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_proj: nc=%d", nc);
+  }
+#undef PJ_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+  h->n_sweep_launches += 1;
+}
+
+template <bool WEIGHTED>
+static void launch_segsum(lfe_ctx* h, int nc, const int32_t* key, const ColPtrs& cols, const uint32_t* perm,
+                          const double* w, int64_t n, double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
+  int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  int blocks = launch_blocks(h, nchunk, 8);
+  bool vec = aligned16(key);
+#define SS_CASE(NC_)                                                                                        \
+  case NC_:                                                                                                 \
+    k_segsum<NC_, WEIGHTED><<<blocks, PJ_T, 0, s>>>(key, cols, perm, w, n, acc, ld_acc, acc_col0, vec);    \
+    break;
+  switch (nc) {
+    SS_CASE(1) SS_CASE(2) SS_CASE(3) SS_CASE(4) SS_CASE(5) SS_CASE(6) SS_CASE(7) SS_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_segsum: nc=%d", nc);
+  }
+#undef SS_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
+static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const ApplyTabs& T, int64_t n, int ldc, int col0,
+                         cudaStream_t s) {
+  int blocks = launch_blocks(h, ceil_div64(n, 256), 8);
+#define AP_CASE(NC_) \
+  case NC_: k_apply<NC_><<<blocks, 256, 0, s>>>(cols, T, n, ldc, col0); break;
+  switch (nc) {
+    AP_CASE(1) AP_CASE(2) AP_CASE(3) AP_CASE(4) AP_CASE(5) AP_CASE(6) AP_CASE(7) AP_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_apply: nc=%d", nc);
+  }
+#undef AP_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
+void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* codes, const int64_t* n_groups,
+                 const int* fe_order, int F, int64_t n, const double* weights, double tol, int max_iter, int min_iter,
+                 int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
+                 cudaStream_t s) {
+  const bool strict_check = (flags & LFE_DEMEAN_STRICT_CHECK) != 0;
+  LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_demean: F=%d out of range [1,%d]", F, LFE_MAX_FE);
+  LFE_REQUIRE(C >= 1, "lfe_demean: C must be >= 1");
+  LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_demean: n out of range");
+  LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
+  {
+    bool seen[LFE_MAX_FE] = {false};
+    for (int j = 0; j < F; ++j) {
+      LFE_REQUIRE(fe_order[j] >= 0 && fe_order[j] < F && !seen[fe_order[j]], "lfe_demean: fe_order is not a permutation");
+      seen[fe_order[j]] = true;
+    }
+  }
+  const bool weighted = weights != nullptr;
+  const bool dist = h->world > 1;
+  *iterations_out = 0;
+  if (max_mean_out) *max_mean_out = 0.0;
+  if (converged_out) *converged_out = 0;
+
+  std::vector<FEState> st(F);
+  // ---- setup: per-FE sorted entry lists, counts, S0 --------------------------------------------
+  {
+    PhaseTimer t(h, s, 5);
+    for (int j = 0; j < F; ++j) {
+      FEState& S = st[j];
+      S.G = n_groups[j];
+      LFE_REQUIRE(S.G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
+      S.identity = prim_is_sorted(h, codes[j], n, s) != 0;
+      if (S.identity) {
+        S.key = codes[j];
+        for (int k = 0; k < F; ++k) S.oth[k] = codes[k];
+        S.w = weights;
+      } else {
+        S.perm.alloc(n, s);
+        S.key_buf.alloc(n, s);
+        prim_argsort_u32(h, (const uint32_t*)codes[j], n, bits_for((uint64_t)(S.G - 1)), S.perm,
+                         (uint32_t*)S.key_buf.p, s);
+        S.key = S.key_buf;
+        for (int k = 0; k < F; ++k) {
+          if (k == j) continue;
+          S.oth_buf[k].alloc(n, s);
+          prim_gather_i32(codes[k], S.perm, n, S.oth_buf[k], s);
+          S.oth[k] = S.oth_buf[k];
+          h->n_launches += 1;
+        }
+        if (weighted) {
+          S.w_buf.alloc(n, s);
+          prim_gather_f64(weights, S.perm, n, S.w_buf, s);
+          S.w = S.w_buf;
+          h->n_launches += 1;
+        }
+      }
+      size_t tab = (size_t)S.G * C;
+      S.alpha.alloc(tab, s); S.S0.alloc(tab, s); S.acc.alloc(tab, s); S.nsum.alloc(S.G, s);
+      S.alpha.zero(); S.S0.zero(); S.acc.zero();
+      S.acc_chk.alloc(S.G, s);
+      S.acc_chk.zero();
+      // unweighted counts
+      {
+        DevBuf<uint32_t> c32(S.G, s);
+        prim_histogram(h, codes[j], n, S.G, c32, s);
+        DevBuf<double>& dst = weighted ? S.cnt_buf : S.nsum;
+        if (weighted) S.cnt_buf.alloc(S.G, s);
+        prim_u32_to_f64(h, c32, S.G, dst, s);
+      }
+      // S0 (weighted sums of every column), column batches of <= PJ_MAXNC
+      for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
+        int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+        ColPtrs cp;
+        for (int c = 0; c < nc; ++c) cp.col[c] = cols[c0 + c];
+        if (weighted) launch_segsum<true>(h, nc, S.key, cp, S.identity ? nullptr : S.perm.p, S.w, n, S.S0, C, c0, s);
+        else launch_segsum<false>(h, nc, S.key, cp, S.identity ? nullptr : S.perm.p, nullptr, n, S.S0, C, c0, s);
+      }
+      if (weighted) {
+        // n_j = sum of weights per group; unweighted y sums for the convergence check
+        S.nsum.zero();
+        ColPtrs cw; cw.col[0] = S.w;
+        launch_segsum<false>(h, 1, S.key, cw, nullptr, nullptr, n, S.nsum, 1, 0, s);
+        S.S0u_buf.alloc(S.G, s);
+        S.S0u_buf.zero();
+        ColPtrs cy; cy.col[0] = cols[0];
+        launch_segsum<false>(h, 1, S.key, cy, S.identity ? nullptr : S.perm.p, nullptr, n, S.S0u_buf, 1, 0, s);
+        S.cnt = S.cnt_buf; S.S0u = S.S0u_buf; S.ld_s0u = 1;
+      } else {
+        S.cnt = S.nsum; S.S0u = S.S0; S.ld_s0u = C;
+      }
+      if (dist && j != local_fe) {
+        PhaseTimer tc(h, s, 13);
+        comm_allreduce(h, S.S0, (int64_t)tab, 0, s);
+        comm_allreduce(h, S.nsum, S.G, 0, s);
+        if (weighted) {
+          comm_allreduce(h, S.cnt_buf, S.G, 0, s);
+          comm_allreduce(h, S.S0u_buf, S.G, 0, s);
+        }
+      }
+    }
+  }
+
+  auto others_of = [&](int j, bool include_all_for_check) {
+    ProjOthers o;
+    o.n = 0;
+    for (int k = 0; k < F; ++k) {
+      if (k == j) continue;
+      o.code[o.n] = st[j].oth[k];
+      o.alpha[o.n] = st[k].alpha;
+      o.n++;
+    }
+    (void)include_all_for_check;
+    return o;
+  };
+
+  DevBuf<double> dmax(1, s);
+  int iterations = 0;
+  bool converged = false;
+  double max_mean = 0.0;
+  for (int it = 1; it <= max_iter; ++it) {
+    if (strict_check) dmax.zero();
+    {
+      PhaseTimer t(h, s, 6);
+      for (int oi = 0; oi < F; ++oi) {
+        int j = fe_order[oi];
+        FEState& S = st[j];
+        if (F > 1) {
+          ProjOthers o = others_of(j, false);
+          for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
+            int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+            if (weighted) launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, s);
+            else launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, s);
+          }
+          if (dist && j != local_fe) {
+            PhaseTimer tc(h, s, 13);
+            comm_allreduce(h, S.acc, S.G * C, 0, s);
+          }
+        }
+        k_finalize<<<launch_blocks(h, ceil_div64(S.G * C, 256), 8), 256, 0, s>>>(S.alpha, S.acc, S.S0, S.nsum, S.G, C,
+                                                                                 strict_check ? dmax.p : nullptr);
+        KERNEL_CHECK();
+        h->n_launches += 1;
+      }
+    }
+    iterations = it;
+    if (it >= min_iter && strict_check) {
+      // true fixed-point test: the largest (weighted) group mean removed during this sweep, all columns
+      PhaseTimer t(h, s, 7);
+      if (dist) comm_allreduce(h, dmax, 1, 1, s);
+      CUDA_CHECK(cudaMemcpyAsync(&max_mean, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (max_mean < tol) {
+        converged = true;
+        break;
+      }
+    } else if (it >= min_iter) {
+      PhaseTimer t(h, s, 7);
+      dmax.zero();
+      for (int j = 0; j < F; ++j) {
+        FEState& S = st[j];
+        if (F > 1) {
+          ProjOthers o = others_of(j, true);
+          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, s);
+          if (dist && j != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
+        }
+        k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
+                                                                           S.G, C, dmax);
+        KERNEL_CHECK();
+        h->n_launches += 1;
+      }
+      if (dist) comm_allreduce(h, dmax, 1, 1, s);
+      CUDA_CHECK(cudaMemcpyAsync(&max_mean, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (max_mean < tol) {
+        converged = true;
+        break;
+      }
+    }
+  }
+
+  // ---- apply the tables to the columns, in place ------------------------------------------------
+  {
+    PhaseTimer t(h, s, 8);
+    ApplyTabs T;
+    T.n = F;
+    for (int j = 0; j < F; ++j) {
+      T.code[j] = codes[j];
+      T.alpha[j] = st[j].alpha;
+    }
+    for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
+      int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+      MutColPtrs mp;
+      for (int c = 0; c < nc; ++c) mp.col[c] = cols[c0 + c];
+      if (n > 0) launch_apply(h, nc, mp, T, n, C, c0, s);
+    }
+  }
+  *iterations_out = iterations;
+  if (max_mean_out) *max_mean_out = max_mean;
+  if (converged_out) *converged_out = converged ? 1 : 0;
+}

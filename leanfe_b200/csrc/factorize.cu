@@ -1,0 +1,395 @@
+// factorize.cu -- group codes, group counts, singleton mask, compaction, row ordering.
+//
+// lfe_factorize maps raw keys to dense int32 codes that are bit-identical to
+// np.unique(keys, return_inverse=True)[1] (order 0) or pandas.factorize(keys)[0] (order 1).
+// Keys are first mapped to an order-preserving uint64 image; if their range is small (the common
+// case for panel ids) a direct-address presence table + scan gives the ranks in three streaming
+// passes; otherwise a stable LSD radix argsort of (key - min) does.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving uint64 image of a key
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+struct KeyIO;
+template <>
+struct KeyIO<LFE_I32> {
+  typedef int32_t T;
+  __device__ static uint64_t enc(T v) { return (uint64_t)((uint32_t)v ^ 0x80000000u); }
+  __device__ static T dec(uint64_t u) { return (T)((uint32_t)u ^ 0x80000000u); }
+};
+template <>
+struct KeyIO<LFE_I64> {
+  typedef int64_t T;
+  __device__ static uint64_t enc(T v) { return (uint64_t)v ^ 0x8000000000000000ull; }
+  __device__ static T dec(uint64_t u) { return (T)(u ^ 0x8000000000000000ull); }
+};
+template <>
+struct KeyIO<LFE_U32> {
+  typedef uint32_t T;
+  __device__ static uint64_t enc(T v) { return v; }
+  __device__ static T dec(uint64_t u) { return (T)u; }
+};
+template <>
+struct KeyIO<LFE_U64> {
+  typedef uint64_t T;
+  __device__ static uint64_t enc(T v) { return v; }
+  __device__ static T dec(uint64_t u) { return u; }
+};
+template <>
+struct KeyIO<LFE_U8> {
+  typedef uint8_t T;
+  __device__ static uint64_t enc(T v) { return v; }
+  __device__ static T dec(uint64_t u) { return (T)u; }
+};
+template <>
+struct KeyIO<LFE_F64> {
+  typedef double T;
+  // -0.0 -> +0.0, every NaN -> the canonical quiet NaN (sorts last, like np.unique)
+  __device__ static uint64_t enc(T v) {
+    if (v != v) return 0xFFF8000000000000ull;
+    v = v + 0.0;
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  }
+  __device__ static T dec(uint64_t u) {
+    if (u == 0xFFF8000000000000ull) return __longlong_as_double(0x7FF8000000000000ll);
+    uint64_t b = (u & 0x8000000000000000ull) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+    return __longlong_as_double((long long)b);
+  }
+};
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_minmax(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                                unsigned long long* __restrict__ mm) {
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long u = KeyIO<DT>::enc(keys[i]);
+    lo = u < lo ? u : lo;
+    hi = u > hi ? u : hi;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, d), b = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_mark(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                              unsigned long long kmin, uint32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flags[KeyIO<DT>::enc(keys[i]) - kmin] = 1u;  // benign race: every writer stores 1
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_lookup(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                                unsigned long long kmin, const uint32_t* __restrict__ rank,
+                                                int32_t* __restrict__ codes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    codes[i] = (int32_t)rank[KeyIO<DT>::enc(keys[i]) - kmin];
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_emit_uniques_direct(const uint32_t* __restrict__ flags,
+                                                             const uint32_t* __restrict__ rank, int64_t range,
+                                                             unsigned long long kmin,
+                                                             typename KeyIO<DT>::T* __restrict__ uniques) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range; i += (int64_t)gridDim.x * blockDim.x)
+    if (flags[i]) uniques[rank[i]] = KeyIO<DT>::dec(kmin + (unsigned long long)i);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_encode_rel(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                                    unsigned long long kmin, uint64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = KeyIO<DT>::enc(keys[i]) - kmin;
+}
+
+__global__ void __launch_bounds__(256) k_boundary_flags(const uint64_t* __restrict__ sk, int64_t n,
+                                                        uint32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (i > 0 && sk[i] != sk[i - 1]) ? 1u : 0u;
+}
+
+// rank_excl = exclusive scan of boundary flags; the rank of position p is rank_excl[p] + flags[p]
+template <int DT>
+__global__ void __launch_bounds__(256) k_scatter_sorted_codes(const uint64_t* __restrict__ sk,
+                                                              const uint32_t* __restrict__ perm,
+                                                              const uint32_t* __restrict__ rank_excl,
+                                                              const uint32_t* __restrict__ flags, int64_t n,
+                                                              unsigned long long kmin, int32_t* __restrict__ codes,
+                                                              typename KeyIO<DT>::T* __restrict__ uniques,
+                                                              int64_t uniques_cap) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t r = rank_excl[i] + flags[i];
+    codes[perm[i]] = (int32_t)r;
+    if (uniques && (i == 0 || flags[i]) && (int64_t)r < uniques_cap) uniques[r] = KeyIO<DT>::dec(sk[i] + kmin);
+  }
+}
+
+// ---- first-appearance relabelling ------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_first_index(const int32_t* __restrict__ codes, int64_t n,
+                                                     uint32_t* __restrict__ first) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicMin(&first[codes[i]], (uint32_t)i);
+}
+__global__ void __launch_bounds__(256) k_invert_perm(const uint32_t* __restrict__ perm, int64_t G,
+                                                     int32_t* __restrict__ newcode) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G; r += (int64_t)gridDim.x * blockDim.x)
+    newcode[perm[r]] = (int32_t)r;
+}
+__global__ void __launch_bounds__(256) k_remap(int32_t* __restrict__ codes, int64_t n,
+                                               const int32_t* __restrict__ newcode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    codes[i] = newcode[codes[i]];
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_permute_small(const T* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                       int64_t G, T* __restrict__ dst) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G; r += (int64_t)gridDim.x * blockDim.x)
+    dst[r] = src[perm[r]];
+}
+
+template <int DT>
+static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int order, int32_t* codes,
+                              void* uniques_v, int64_t uniques_cap, cudaStream_t s) {
+  typedef typename KeyIO<DT>::T T;
+  const T* keys = (const T*)keys_v;
+  T* uniques = (T*)uniques_v;
+  if (n == 0) return 0;
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  DevBuf<unsigned long long> mm(2, s);
+  unsigned long long init[2] = {~0ull, 0ull};
+  CUDA_CHECK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  k_minmax<DT><<<blocks, 256, 0, s>>>(keys, n, mm);
+  KERNEL_CHECK();
+  unsigned long long hmm[2];
+  CUDA_CHECK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  h->n_launches += 1;
+  const unsigned long long kmin = hmm[0];
+  const unsigned long long span = hmm[1] - hmm[0];  // range - 1
+  int64_t G = 0;
+  unsigned long long direct_limit = (unsigned long long)(16 * n > (1 << 20) ? 16 * n : (1 << 20));
+  if (direct_limit > (1ull << 28)) direct_limit = 1ull << 28;
+  DevBuf<uint32_t> total(1, s);
+  if (span < direct_limit) {
+    int64_t range = (int64_t)span + 1;
+    DevBuf<uint32_t> flags(range, s), rank(range, s);
+    flags.zero();
+    k_mark<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, flags);
+    KERNEL_CHECK();
+    prim_exclusive_scan_u32(h, flags, rank, range, total, s);
+    k_lookup<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, rank, codes);
+    KERNEL_CHECK();
+    uint32_t ht = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&ht, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    G = ht;
+    h->n_launches += 2;
+    if (uniques && G <= uniques_cap) {
+      int b2 = launch_blocks(h, ceil_div64(range, 256 * 4), 8);
+      k_emit_uniques_direct<DT><<<b2, 256, 0, s>>>(flags, rank, range, kmin, uniques);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
+  } else {
+    DevBuf<uint64_t> rel(n, s), sk(n, s);
+    DevBuf<uint32_t> perm(n, s), flags(n, s), rank(n, s);
+    k_encode_rel<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, rel);
+    KERNEL_CHECK();
+    prim_argsort_u64(h, rel, n, bits_for(span), perm, sk, s);
+    k_boundary_flags<<<blocks, 256, 0, s>>>(sk, n, flags);
+    KERNEL_CHECK();
+    prim_exclusive_scan_u32(h, flags, rank, n, total, s);
+    k_scatter_sorted_codes<DT><<<blocks, 256, 0, s>>>(sk, perm, rank, flags, n, kmin, codes, uniques, uniques_cap);
+    KERNEL_CHECK();
+    uint32_t ht = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&ht, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    G = (int64_t)ht + 1;
+    h->n_launches += 3;
+  }
+  if (order == LFE_ORDER_FIRST && G > 1) {
+    DevBuf<uint32_t> first(G, s), gperm(G, s);
+    DevBuf<int32_t> newcode(G, s);
+    CUDA_CHECK(cudaMemsetAsync(first.p, 0xFF, (size_t)G * sizeof(uint32_t), s));
+    k_first_index<<<blocks, 256, 0, s>>>(codes, n, first);
+    KERNEL_CHECK();
+    prim_argsort_u32(h, first, G, bits_for((uint64_t)n), gperm, nullptr, s);
+    int bg = launch_blocks(h, ceil_div64(G, 256), 8);
+    k_invert_perm<<<bg, 256, 0, s>>>(gperm, G, newcode);
+    KERNEL_CHECK();
+    k_remap<<<blocks, 256, 0, s>>>(codes, n, newcode);
+    KERNEL_CHECK();
+    h->n_launches += 3;
+    if (uniques && G <= uniques_cap) {
+      DevBuf<T> tmp(G, s);
+      CUDA_CHECK(cudaMemcpyAsync(tmp.p, uniques, (size_t)G * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      k_permute_small<T><<<bg, 256, 0, s>>>(tmp, gperm, G, uniques);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
+  }
+  return G;
+}
+
+int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
+                           void* uniques, int64_t uniques_cap, cudaStream_t s) {
+  PhaseTimer t(h, s, 0);
+  switch (key_dtype) {
+    case LFE_I32: return factorize_impl<LFE_I32>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    case LFE_I64: return factorize_impl<LFE_I64>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    case LFE_U32: return factorize_impl<LFE_U32>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    case LFE_U64: return factorize_impl<LFE_U64>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    case LFE_F64: return factorize_impl<LFE_F64>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    case LFE_U8: return factorize_impl<LFE_U8>(h, keys, n, order, codes, uniques, uniques_cap, s);
+    default: LFE_THROW(LFE_ERR_ARG, "lfe_factorize: unknown key dtype %d", key_dtype);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// singleton mask  (polars_impl.py:478-482)
+// ---------------------------------------------------------------------------------------------
+struct CodePtrs {
+  const int32_t* code[LFE_MAX_FE];
+  const uint32_t* cnt[LFE_MAX_FE];
+};
+
+__global__ void __launch_bounds__(256) k_singleton_mask(CodePtrs P, int F, int64_t n, uint8_t* __restrict__ keep,
+                                                        unsigned long long* __restrict__ n_keep) {
+  unsigned int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bool k = true;
+    for (int j = 0; j < F; ++j) k = k && (P.cnt[j][P.code[j][i]] > 1u);
+    keep[i] = k ? 1 : 0;
+    local += k ? 1u : 0u;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_keep, (unsigned long long)local);
+}
+
+// after the drop: a group survives iff it still has a kept row
+__global__ void __launch_bounds__(256) k_mark_kept_groups(const int32_t* __restrict__ code,
+                                                          const uint8_t* __restrict__ keep, int64_t n,
+                                                          uint32_t* __restrict__ present) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (keep[i]) present[code[i]] = 1u;
+}
+__global__ void __launch_bounds__(256) k_count_nonzero(const uint32_t* __restrict__ v, int64_t n,
+                                                       unsigned long long* __restrict__ out) {
+  unsigned int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    local += v[i] ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
+                         uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 1);
+  LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_singleton_mask: F=%d out of range", F);
+  std::vector<DevBuf<uint32_t>> cnts(F);
+  CodePtrs P;
+  for (int j = 0; j < F; ++j) {
+    cnts[j].alloc((size_t)n_groups[j], s);
+    prim_histogram(h, codes[j], n, n_groups[j], cnts[j], s);
+    P.code[j] = codes[j];
+    P.cnt[j] = cnts[j];
+  }
+  DevBuf<unsigned long long> acc(1 + F, s);
+  acc.zero();
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  if (n > 0) {
+    k_singleton_mask<<<blocks, 256, 0, s>>>(P, F, n, keep, acc);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  }
+  if (fe_dims_out) {
+    for (int j = 0; j < F; ++j) {
+      CUDA_CHECK(cudaMemsetAsync(cnts[j].p, 0, (size_t)n_groups[j] * sizeof(uint32_t), s));
+      if (n > 0) {
+        k_mark_kept_groups<<<blocks, 256, 0, s>>>(codes[j], keep, n, cnts[j]);
+        KERNEL_CHECK();
+        int bg = launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8);
+        k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], acc.p + 1 + j);
+        KERNEL_CHECK();
+        h->n_launches += 2;
+      }
+    }
+  }
+  std::vector<unsigned long long> hacc(1 + F);
+  CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, (1 + F) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  *n_keep_out = (int64_t)hacc[0];
+  if (fe_dims_out)
+    for (int j = 0; j < F; ++j) fe_dims_out[j] = (int64_t)hacc[1 + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable compaction
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_keep_to_u32(const uint8_t* __restrict__ keep, int64_t n,
+                                                     uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = keep[i];
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_compact(const T* __restrict__ src, const uint8_t* __restrict__ keep,
+                                                 const uint32_t* __restrict__ pos, int64_t n, T* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (keep[i]) dst[pos[i]] = src[i];
+}
+
+void compact_impl(lfe_ctx* h, const uint8_t* keep, int64_t n, const double* const* f64_in, double* const* f64_out,
+                  int C, const int32_t* const* i32_in, int32_t* const* i32_out, int K, cudaStream_t s) {
+  PhaseTimer t(h, s, 2);
+  if (n <= 0) return;
+  DevBuf<uint32_t> pos(n, s);
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  k_keep_to_u32<<<blocks, 256, 0, s>>>(keep, n, pos);
+  KERNEL_CHECK();
+  prim_exclusive_scan_u32(h, pos, pos, n, nullptr, s);
+  for (int c = 0; c < C; ++c) {
+    k_compact<double><<<blocks, 256, 0, s>>>(f64_in[c], keep, pos, n, f64_out[c]);
+    KERNEL_CHECK();
+  }
+  for (int c = 0; c < K; ++c) {
+    k_compact<int32_t><<<blocks, 256, 0, s>>>(i32_in[c], keep, pos, n, i32_out[c]);
+    KERNEL_CHECK();
+  }
+  h->n_launches += 1 + C + K;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row ordering
+// ---------------------------------------------------------------------------------------------
+void sort_rows_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t n_groups, int32_t* perm_out,
+                    int* already_sorted_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 3);
+  int sorted = prim_is_sorted(h, codes, n, s);
+  if (already_sorted_out) *already_sorted_out = sorted;
+  if (sorted) {
+    prim_iota_u32((uint32_t*)perm_out, n, s);
+    h->n_launches += 1;
+    return;
+  }
+  prim_argsort_u32(h, (const uint32_t*)codes, n, bits_for((uint64_t)(n_groups > 0 ? n_groups - 1 : 0)),
+                   (uint32_t*)perm_out, nullptr, s);
+}
+
+void gather_impl(lfe_ctx* h, const int32_t* perm, int64_t n, const double* const* f64_in, double* const* f64_out,
+                 int C, const int32_t* const* i32_in, int32_t* const* i32_out, int K, cudaStream_t s) {
+  PhaseTimer t(h, s, 4);
+  for (int c = 0; c < C; ++c) prim_gather_f64(f64_in[c], (const uint32_t*)perm, n, f64_out[c], s);
+  for (int c = 0; c < K; ++c) prim_gather_i32(i32_in[c], (const uint32_t*)perm, n, i32_out[c], s);
+  h->n_launches += C + K;
+}

@@ -1,0 +1,399 @@
+// prims.cu -- device-wide primitives written for this library: exclusive scan, stable LSD radix
+// argsort, histogram, sortedness test, gathers.  All launches size their grids in multiples of the
+// SM count (148 on B200) or one tile per CTA for the tiled sort passes.
+#include "common.cuh"
+
+int bits_for(uint64_t v) {
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
+}
+
+int launch_blocks(lfe_ctx* h, int64_t work_items, int per_sm) {
+  int64_t cap = (int64_t)h->sm_count * per_sm;
+  if (work_items < 1) work_items = 1;
+  return (int)(work_items < cap ? work_items : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (uint32)
+// ---------------------------------------------------------------------------------------------
+constexpr int SC_T = 256;
+constexpr int SC_I = 8;
+constexpr int SC_TILE = SC_T * SC_I;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t ws[SC_T / 32];
+  __shared__ uint32_t tot;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = lane < SC_T / 32 ? ws[lane] : 0;
+    uint32_t xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
+      if (lane >= d) xi += o;
+    }
+    if (lane < SC_T / 32) ws[lane] = xi - x;
+    if (lane == 31) tot = xi;
+  }
+  __syncthreads();
+  uint32_t r = ws[w] + inc - v;
+  *total = tot;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SC_T) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n,
+                                                      uint32_t* __restrict__ tile_sums) {
+  int64_t base = (int64_t)blockIdx.x * SC_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_I; ++i) {
+    int64_t idx = base + (int64_t)i * SC_T + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  __shared__ uint32_t ws[SC_T / 32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < SC_T / 32; ++i) t += ws[i];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+// scans one tile; thread t owns SC_I consecutive items
+__global__ void __launch_bounds__(SC_T) k_scan_tile(const uint32_t* in, uint32_t* out, int64_t n,
+                                                    const uint32_t* __restrict__ tile_offsets,
+                                                    uint32_t* total_out) {
+  int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_I;
+  uint32_t v[SC_I];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_I; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    s += v[i];
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan(s, &tot);
+  uint32_t off = tile_offsets ? tile_offsets[blockIdx.x] : 0u;
+  uint32_t run = off + ex;
+#pragma unroll
+  for (int i = 0; i < SC_I; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+  if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = off + tot;
+}
+
+void prim_exclusive_scan_u32(lfe_ctx* h, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* total_dev,
+                             cudaStream_t s) {
+  if (n <= 0) {
+    if (total_dev) CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), s));
+    return;
+  }
+  int64_t nt = ceil_div64(n, SC_TILE);
+  if (nt == 1) {
+    k_scan_tile<<<1, SC_T, 0, s>>>(in, out, n, nullptr, total_dev);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    return;
+  }
+  DevBuf<uint32_t> sums(nt, s);
+  k_scan_reduce<<<(int)nt, SC_T, 0, s>>>(in, n, sums);
+  KERNEL_CHECK();
+  prim_exclusive_scan_u32(h, sums, sums, nt, nullptr, s);
+  k_scan_tile<<<(int)nt, SC_T, 0, s>>>(in, out, n, sums, total_dev);
+  KERNEL_CHECK();
+  h->n_launches += 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix argsort, 8 bits per pass
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_T = 256;
+constexpr int RS_NW = RS_T / 32;
+constexpr int RS_I = 16;
+constexpr int RS_TILE = RS_T * RS_I;
+constexpr int RS_BINS = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift,
+                                                     uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t cnt[RS_BINS];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < RS_I; ++i) {
+    int64_t idx = base + (int64_t)i * RS_T + threadIdx.x;
+    bool valid = idx < n;
+    uint32_t d = valid ? (uint32_t)((keys[idx] >> shift) & 0xFF) : (256u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&cnt[d], __popc(peers));
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_T) k_radix_scatter(const KeyT* __restrict__ keys_in,
+                                                        const uint32_t* __restrict__ vals_in,
+                                                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                        int64_t n, int shift, const uint32_t* __restrict__ offsets,
+                                                        int nblocks) {
+  __shared__ uint32_t wcnt[RS_NW][RS_BINS];
+  __shared__ uint32_t dbase[RS_BINS];
+  for (int i = threadIdx.x; i < RS_NW * RS_BINS; i += RS_T) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_I);
+  KeyT k[RS_I];
+  uint32_t v[RS_I];
+  uint32_t rk[RS_I];
+#pragma unroll
+  for (int r = 0; r < RS_I; ++r) {
+    int64_t idx = wbase + r * 32 + lane;
+    bool valid = idx < n;
+    k[r] = valid ? keys_in[idx] : (KeyT)0;
+    v[r] = valid ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_I; ++r) {
+    int64_t idx = wbase + r * 32 + lane;
+    bool valid = idx < n;
+    uint32_t d = valid ? (uint32_t)((k[r] >> shift) & 0xFF) : (256u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t base = valid ? wcnt[warp][d] : 0u;
+    __syncwarp();
+    rk[r] = base + __popc(peers & lt);
+    if (valid && lane == (__ffs(peers) - 1)) wcnt[warp][d] = base + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    int t = threadIdx.x;  // RS_T == RS_BINS
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_NW; ++w) {
+      uint32_t c = wcnt[w][t];
+      wcnt[w][t] = run;
+      run += c;
+    }
+    dbase[t] = offsets[(size_t)t * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_I; ++r) {
+    int64_t idx = wbase + r * 32 + lane;
+    if (idx < n) {
+      uint32_t d = (uint32_t)((k[r] >> shift) & 0xFF);
+      uint32_t pos = dbase[d] + wcnt[warp][d] + rk[r];
+      if (keys_out) keys_out[pos] = k[r];
+      vals_out[pos] = v[r];
+    }
+  }
+}
+
+__global__ void k_iota(uint32_t* p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = (uint32_t)i;
+}
+void prim_iota_u32(uint32_t* p, int64_t n, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t nb = ceil_div64(n, 1024);
+  int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
+  k_iota<<<blocks, 256, 0, s>>>(p, n);
+  KERNEL_CHECK();
+}
+
+template <typename KeyT>
+static void argsort_impl(lfe_ctx* h, const KeyT* keys, int64_t n, int key_bits, uint32_t* perm_out,
+                         KeyT* keys_sorted_out, cudaStream_t s) {
+  if (n <= 0) return;
+  int npass = (key_bits + 7) / 8;
+  if (npass == 0) {
+    prim_iota_u32(perm_out, n, s);
+    if (keys_sorted_out) CUDA_CHECK(cudaMemcpyAsync(keys_sorted_out, keys, n * sizeof(KeyT), cudaMemcpyDeviceToDevice, s));
+    h->n_launches += 1;
+    return;
+  }
+  int nblocks = (int)ceil_div64(n, RS_TILE);
+  DevBuf<uint32_t> hist((size_t)RS_BINS * nblocks, s);
+  DevBuf<KeyT> ka(npass > 1 ? n : 0, s), kb(npass > 2 ? n : 0, s);
+  DevBuf<uint32_t> va(npass > 1 ? n : 0, s);
+  const KeyT* kin = keys;
+  const uint32_t* vin = nullptr;
+  for (int p = 0; p < npass; ++p) {
+    bool last = (p == npass - 1);
+    // value ping-pong so that the last pass lands in perm_out
+    uint32_t* vout = (((npass - 1 - p) & 1) == 0) ? perm_out : va.p;
+    KeyT* kout = last ? keys_sorted_out : ((p & 1) == 0 ? ka.p : kb.p);
+    int shift = p * 8;
+    k_radix_hist<KeyT><<<nblocks, RS_T, 0, s>>>(kin, n, shift, hist, nblocks);
+    KERNEL_CHECK();
+    prim_exclusive_scan_u32(h, hist, hist, (int64_t)RS_BINS * nblocks, nullptr, s);
+    k_radix_scatter<KeyT><<<nblocks, RS_T, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    kin = kout;
+    vin = vout;
+  }
+}
+
+void prim_argsort_u32(lfe_ctx* h, const uint32_t* keys, int64_t n, int key_bits, uint32_t* perm_out,
+                      uint32_t* keys_sorted_out, cudaStream_t s) {
+  argsort_impl<uint32_t>(h, keys, n, key_bits, perm_out, keys_sorted_out, s);
+}
+void prim_argsort_u64(lfe_ctx* h, const uint64_t* keys, int64_t n, int key_bits, uint32_t* perm_out,
+                      uint64_t* keys_sorted_out, cudaStream_t s) {
+  argsort_impl<uint64_t>(h, keys, n, key_bits, perm_out, keys_sorted_out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// histogram of dense codes
+// ---------------------------------------------------------------------------------------------
+constexpr int HG_SMEM_BINS = 8192;
+
+__global__ void __launch_bounds__(256) k_hist_smem(const int32_t* __restrict__ codes, int64_t n, int G,
+                                                   uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sh[];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nround = ceil_div64(n, stride);
+  for (int64_t r = 0; r < nround; ++r) {
+    int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    uint32_t c = valid ? (uint32_t)__ldcs(codes + i) : (0x80000000u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&sh[c], __popc(peers));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x)
+    if (sh[i]) atomicAdd(&counts[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) k_hist_global(const int32_t* __restrict__ codes, int64_t n,
+                                                     uint32_t* __restrict__ counts) {
+  int lane = threadIdx.x & 31;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nround = ceil_div64(n, stride);
+  for (int64_t r = 0; r < nround; ++r) {
+    int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    uint32_t c = valid ? (uint32_t)__ldcs(codes + i) : (0x80000000u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&counts[c], __popc(peers));
+  }
+}
+
+void prim_histogram(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, uint32_t* counts, cudaStream_t s) {
+  CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)G * sizeof(uint32_t), s));
+  if (n <= 0) return;
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 8);
+  if (G <= HG_SMEM_BINS) {
+    k_hist_smem<<<blocks, 256, (size_t)G * sizeof(uint32_t), s>>>(codes, n, (int)G, counts);
+  } else {
+    k_hist_global<<<blocks, 256, 0, s>>>(codes, n, counts);
+  }
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sortedness
+// ---------------------------------------------------------------------------------------------
+__global__ void k_is_sorted(const int32_t* __restrict__ codes, int64_t n, int* __restrict__ flag) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bad |= (codes[i] < codes[i - 1]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+
+int prim_is_sorted(lfe_ctx* h, const int32_t* codes, int64_t n, cudaStream_t s) {
+  if (n <= 1) return 1;
+  DevBuf<int> flag(1, s);
+  flag.zero();
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 8);
+  k_is_sorted<<<blocks, 256, 0, s>>>(codes, n, flag);
+  KERNEL_CHECK();
+  h->n_launches += 1;
+  int hflag = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  return hflag == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gathers: dst[i] = src[perm[i]]   (4 independent loads in flight per thread)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather(const T* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                int64_t n, T* __restrict__ dst) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    uint32_t p0 = __ldcs(perm + i), p1 = __ldcs(perm + i + stride), p2 = __ldcs(perm + i + 2 * stride),
+             p3 = __ldcs(perm + i + 3 * stride);
+    T a = src[p0], b = src[p1], c = src[p2], d = src[p3];
+    __stcs(dst + i, a);
+    __stcs(dst + i + stride, b);
+    __stcs(dst + i + 2 * stride, c);
+    __stcs(dst + i + 3 * stride, d);
+  }
+  for (; i < n; i += stride) dst[i] = src[perm[i]];
+}
+
+void prim_gather_f64(const double* src, const uint32_t* perm, int64_t n, double* dst, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t nb = ceil_div64(n, 256 * 4);
+  int blocks = (int)(nb < 148 * 16 ? nb : 148 * 16);
+  k_gather<double><<<blocks, 256, 0, s>>>(src, perm, n, dst);
+  KERNEL_CHECK();
+}
+void prim_gather_i32(const int32_t* src, const uint32_t* perm, int64_t n, int32_t* dst, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t nb = ceil_div64(n, 256 * 4);
+  int blocks = (int)(nb < 148 * 16 ? nb : 148 * 16);
+  k_gather<int32_t><<<blocks, 256, 0, s>>>(src, perm, n, dst);
+  KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small conversions
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cvt_u32_f64(const uint32_t* __restrict__ in, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];
+}
+__global__ void __launch_bounds__(256) k_cvt_f64_u32(const double* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (uint32_t)in[i];
+}
+void prim_u32_to_f64(lfe_ctx* h, const uint32_t* in, int64_t n, double* out, cudaStream_t s) {
+  if (n <= 0) return;
+  k_cvt_u32_f64<<<launch_blocks(h, ceil_div64(n, 1024), 8), 256, 0, s>>>(in, n, out);
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+void prim_f64_to_u32(lfe_ctx* h, const double* in, int64_t n, uint32_t* out, cudaStream_t s) {
+  if (n <= 0) return;
+  k_cvt_f64_u32<<<launch_blocks(h, ceil_div64(n, 1024), 8), 256, 0, s>>>(in, n, out);
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}

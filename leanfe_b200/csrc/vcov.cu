@@ -1,0 +1,399 @@
+// vcov.cu -- residuals, R^2 ingredients and IID / HC1 / clustered sandwich standard errors.
+// Reference: python/leanfe/polars_impl.py:229-232, 281-283 and python/leanfe/std_errors.py:183-441.
+//
+// One streaming pass computes r = y - b0 - X beta, sum r^2, sum w r^2 and the shifted moments of y.
+// HC1 reuses the Gram kernels with omega = w r^2.  Cluster scores S_g = sum_{i in g} w x_i r_i are a
+// by-key reduction (segmented when the cluster is the row sort key, RED.ADD.F64 otherwise) into a
+// column-major G x k table whose Gram is the meat.  The k x k sandwich algebra runs in one CTA.
+#include "common.cuh"
+#include "segreduce.cuh"
+
+void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* w, const double* r,
+               int add_intercept, double* gram_out, cudaStream_t s);
+int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
+                           void* uniques, int64_t uniques_cap, cudaStream_t s);
+void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);
+
+constexpr int RV_MAXK = 96;
+struct XCols {
+  const double* col[RV_MAXK];
+};
+
+// partials[block][5] = { sum r^2, sum w r^2, sum (y-c), sum (y-c)^2, 0 }
+__global__ void __launch_bounds__(256) k_resid(const double* __restrict__ y, XCols X, int k,
+                                               const double* __restrict__ beta_full, const double* __restrict__ w,
+                                               int64_t n, double* __restrict__ resid, double* __restrict__ partials,
+                                               int use_shift) {
+  __shared__ double sb[RV_MAXK + 1];
+  for (int j = threadIdx.x; j <= k; j += blockDim.x) sb[j] = beta_full[j];
+  __syncthreads();
+  const double c = use_shift ? y[0] : 0.0;  // multi-rank: a common shift (0) keeps the moments summable
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double yi = __ldcs(y + i);
+    double r = yi - sb[0];
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) r = fma(-sb[j + 1], __ldcs(X.col[j] + i), r);
+    __stcs(resid + i, r);
+    double r2 = r * r;
+    a0 += r2;
+    a1 += w ? __ldcs(w + i) * r2 : r2;
+    double d = yi - c;
+    a2 += d;
+    a3 = fma(d, d, a3);
+  }
+  __shared__ double sh[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if (lane == 0) { sh[warp][0] = a0; sh[warp][1] = a1; sh[warp][2] = a2; sh[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0;
+    for (int q = 0; q < 8; ++q) v += sh[q][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+}
+
+// stats = { rss, tss, sum w r^2, 0 }
+__global__ void k_resid_final(const double* __restrict__ partials, int nblocks, double n_local,
+                              double* __restrict__ raw /*4*/) {
+  if (threadIdx.x < 4) {
+    double v = 0;
+    for (int b = 0; b < nblocks; ++b) v += partials[(size_t)b * 4 + threadIdx.x];
+    raw[threadIdx.x] = v;
+  }
+}
+__global__ void k_stats_from_raw(const double* __restrict__ raw, double n_total, double* __restrict__ stats) {
+  if (threadIdx.x == 0) {
+    stats[0] = raw[0];
+    stats[1] = raw[3] - raw[2] * raw[2] / n_total;  // sum (y - ybar)^2 from moments shifted by c = y[0]
+    stats[2] = raw[1];
+    stats[3] = 0.0;
+  }
+}
+
+// S[c * G + key] += w * x_c * r      (any key order; runs of equal keys are merged first)
+template <int NC>
+__global__ void __launch_bounds__(PJ_T) k_scores(const int32_t* __restrict__ key, ColPtrs X,
+                                                 const double* __restrict__ r, const double* __restrict__ w,
+                                                 int64_t n, double* __restrict__ S, int64_t G, int col0, bool vec_codes) {
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    int k[PJ_I];
+    load4_i32(key, base, n, vec_codes, k);
+    double v[PJ_I][NC];
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e) {
+      bool valid = base + e < n;
+      double rr = valid ? __ldcs(r + base + e) : 0.0;
+      if (w && valid) rr *= __ldcs(w + base + e);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[e][c] = valid ? __ldcs(X.col[c] + base + e) * rr : 0.0;
+    }
+    segmented_flush<NC>(k, v, S, 1, col0, G);
+  }
+}
+
+__global__ void k_combine_keys(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t Gb, int64_t n,
+                               uint64_t* __restrict__ out, int first) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (first ? (uint64_t)a[i] : out[i]) * (uint64_t)Gb + (uint64_t)b[i];
+}
+
+__global__ void __launch_bounds__(256) k_count_present(const int32_t* __restrict__ codes, int64_t n,
+                                                       uint32_t* __restrict__ present) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    present[codes[i]] = 1u;
+}
+__global__ void __launch_bounds__(256) k_sum_u32(const uint32_t* __restrict__ v, int64_t n,
+                                                 unsigned long long* __restrict__ out) {
+  unsigned int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    local += v[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+// V += sign * B * M * B      (k x k, one CTA, tmp = k*k scratch)
+__global__ void __launch_bounds__(256) k_sandwich(const double* __restrict__ B, const double* __restrict__ M, int k,
+                                                  double sign, double* __restrict__ tmp, double* __restrict__ V) {
+  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+    int i = idx / k, j = idx % k;
+    double s = 0;
+    for (int q = 0; q < k; ++q) s = fma(B[i * k + q], M[q * k + j], s);
+    tmp[idx] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+    int i = idx / k, j = idx % k;
+    double s = 0;
+    for (int q = 0; q < k; ++q) s = fma(tmp[i * k + q], B[q * k + j], s);
+    V[idx] += sign * s;
+  }
+}
+// vcov = scale * V ; se = sqrt(max(diag, 0))
+__global__ void k_scale_se(const double* __restrict__ V, int k, double scale, const double* __restrict__ scale_dev,
+                           int scale_idx, double scale_div, double* __restrict__ vcov_out, double* __restrict__ se_out) {
+  double sc = scale;
+  if (scale_dev) sc *= scale_dev[scale_idx] / scale_div;
+  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+    double v = sc * V[idx];
+    if (vcov_out) vcov_out[idx] = v;
+    if (idx / k == idx % k) se_out[idx / k] = sqrt(fmax(v, 0.0));
+  }
+}
+
+static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* const* xcols, int k, const double* resid,
+                        const double* w, int64_t n, double* meat_dev, cudaStream_t s) {
+  DevBuf<double> S((size_t)G * k, s);
+  S.zero();
+  int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  int blocks = launch_blocks(h, nchunk, 8);
+  bool vec = (((uintptr_t)cl) & 15) == 0;
+  for (int c0 = 0; c0 < k; c0 += PJ_MAXNC) {
+    int nc = k - c0 < PJ_MAXNC ? k - c0 : PJ_MAXNC;
+    ColPtrs cp;
+    for (int c = 0; c < nc; ++c) cp.col[c] = xcols[c0 + c];
+#define SC_CASE(NC_) \
+  case NC_: k_scores<NC_><<<blocks, PJ_T, 0, s>>>(cl, cp, resid, w, n, S, G, c0, vec); break;
+    switch (nc) {
+      SC_CASE(1) SC_CASE(2) SC_CASE(3) SC_CASE(4) SC_CASE(5) SC_CASE(6) SC_CASE(7) SC_CASE(8)
+    }
+#undef SC_CASE
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  }
+  if (h->world > 1) comm_allreduce(h, S, G * k, 0, s);
+  std::vector<const double*> sc(k);
+  for (int c = 0; c < k; ++c) sc[c] = S.p + (size_t)c * G;
+  gram_core(h, sc.data(), k, G, nullptr, nullptr, 0, meat_dev, s);
+}
+
+static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, cudaStream_t s) {
+  DevBuf<uint32_t> present(G, s);
+  present.zero();
+  DevBuf<unsigned long long> tot(1, s);
+  tot.zero();
+  int blocks = launch_blocks(h, ceil_div64(n, 1024), 8);
+  if (n > 0) {
+    k_count_present<<<blocks, 256, 0, s>>>(codes, n, present);
+    KERNEL_CHECK();
+  }
+  if (h->world > 1) {
+    // presence flags are combined across ranks through a double buffer (counts stay exact: 0/1 sums < 2^53)
+    DevBuf<double> pd(G, s);
+    prim_u32_to_f64(h, present, G, pd, s);
+    comm_allreduce(h, pd, G, 1, s);
+    prim_f64_to_u32(h, pd, G, present, s);
+  }
+  k_sum_u32<<<launch_blocks(h, ceil_div64(G, 1024), 8), 256, 0, s>>>(present, G, tot);
+  KERNEL_CHECK();
+  h->n_launches += 2;
+  unsigned long long ht = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&ht, tot.p, sizeof(ht), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  return (int64_t)ht;
+}
+
+
+// Clustered sandwich shared by the row-level and the YOCO paths.  r = per-row "score residual"
+// (resid, or e0_g = sum_y - n yhat on compressed rows), w optional multiplier.  V must be zeroed.
+static void cluster_sandwich(lfe_ctx* h, const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W,
+                             const double* const* xc, int k, const double* r, const double* w, int64_t n,
+                             const double* Binv, int ssc, int64_t n_obs, int64_t df_resid, double* V, double* tmp,
+                             double* meat, double* se_out, double* vcov_out, int64_t* n_clusters_out, cudaStream_t s) {
+  if (W == 1) {
+    // std_errors.py:289-347 / compress.py:922-953
+    int64_t G = count_present(h, cl_codes[0], n, n_cl_groups[0], s);
+    if (n_clusters_out) n_clusters_out[0] = G;
+    LFE_REQUIRE(G > 1, "clustered vcov: a single cluster (division by zero in G/(G-1))");
+    scores_meat(h, cl_codes[0], n_cl_groups[0], xc, k, r, w, n, meat, s);
+    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+    KERNEL_CHECK();
+    double adj = (double)G / (double)(G - 1);
+    if (ssc) adj *= (double)(n_obs - 1) / (double)df_resid;
+    k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    return;
+  }
+  // multiway, Cameron-Gelbach-Miller inclusion-exclusion      std_errors.py:354-441 / compress.py:956-1042
+  LFE_REQUIRE(h->world == 1, "multiway clustering is single-GPU only");
+  int64_t Gmin = -1;
+  DevBuf<uint64_t> ckey(n, s);
+  DevBuf<int32_t> ccode(n, s);
+  int kblocks = launch_blocks(h, ceil_div64(n, 1024), 8);
+  for (int mask = 1; mask < (1 << W); ++mask) {
+    int size = __builtin_popcount(mask);
+    double sign = (size & 1) ? 1.0 : -1.0;
+    int64_t G, Gcap;
+    const int32_t* codes;
+    if (size == 1) {
+      int a = __builtin_ctz(mask);
+      codes = cl_codes[a];
+      Gcap = n_cl_groups[a];
+      G = count_present(h, codes, n, Gcap, s);
+      if (n_clusters_out) n_clusters_out[a] = G;
+      Gmin = (Gmin < 0 || G < Gmin) ? G : Gmin;
+    } else {
+      int first = 1, prev = -1;
+      double space = 1.0;
+      for (int a = 0; a < W; ++a) {
+        if (!(mask & (1 << a))) continue;
+        space *= (double)n_cl_groups[a];
+        if (prev < 0) { prev = a; continue; }
+        k_combine_keys<<<kblocks, 256, 0, s>>>(cl_codes[prev], cl_codes[a], n_cl_groups[a], n, ckey, first);
+        KERNEL_CHECK();
+        h->n_launches += 1;
+        first = 0;
+      }
+      LFE_REQUIRE(space < 1.8e19, "cluster intersection key space overflows 64 bits");
+      G = factorize_dispatch(h, ckey, LFE_U64, n, LFE_ORDER_SORTED, ccode, nullptr, 0, s);
+      Gcap = G;
+      codes = ccode;
+    }
+    if (G <= 1) continue;
+    scores_meat(h, codes, Gcap, xc, k, r, w, n, meat, s);
+    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, sign, tmp, V);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  }
+  double adj = 1.0;
+  if (Gmin > 2) adj *= (double)Gmin / (double)(Gmin - 1);
+  if (ssc) adj *= (double)(n_obs - 1) / (double)df_resid;
+  k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
+void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, const double* beta_full,
+                     const double* Binv, int vcov_kind, const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W,
+                     const double* weights, int ssc, int64_t n_obs, int64_t df_resid, double* se_out, double* vcov_out,
+                     double* stats_out, double* resid_out, int64_t* n_clusters_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 11);
+  LFE_REQUIRE(k >= 0 && k <= RV_MAXK, "lfe_resid_vcov: k=%d out of range", k);
+  LFE_REQUIRE(vcov_kind >= 0 && vcov_kind <= 2, "lfe_resid_vcov: unknown vcov kind %d", vcov_kind);
+  LFE_REQUIRE(n >= 1, "lfe_resid_vcov: no rows");
+  if (vcov_kind == LFE_VCOV_CLUSTER) LFE_REQUIRE(W >= 1 && W <= LFE_MAX_CLUSTER_WAYS, "lfe_resid_vcov: cluster_cols required (1..%d ways)", LFE_MAX_CLUSTER_WAYS);
+  DevBuf<double> resid_buf;
+  double* resid = resid_out;
+  if (!resid) {
+    resid_buf.alloc(n, s);
+    resid = resid_buf;
+  }
+  XCols X;
+  for (int j = 0; j < k; ++j) X.col[j] = cols[1 + j];
+  int blocks = launch_blocks(h, ceil_div64(n, 512), 4);
+  DevBuf<double> partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
+  k_resid<<<blocks, 256, 0, s>>>(cols[0], X, k, beta_full, weights, n, resid, partials, h->world == 1 ? 1 : 0);
+  KERNEL_CHECK();
+  k_resid_final<<<1, 32, 0, s>>>(partials, blocks, (double)n, raw);
+  KERNEL_CHECK();
+  if (h->world > 1) comm_allreduce(h, raw, 4, 0, s);
+  double* stats = stats_out ? stats_out : stats_local.p;
+  k_stats_from_raw<<<1, 32, 0, s>>>(raw, (double)n_obs, stats);
+  KERNEL_CHECK();
+  h->n_launches += 3;
+  if (k == 0) return;
+
+  DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
+  V.zero();
+  std::vector<const double*> xc(k);
+  for (int j = 0; j < k; ++j) xc[j] = cols[1 + j];
+
+  if (vcov_kind == LFE_VCOV_IID) {
+    // se = sqrt(max(sum(w r^2)/df * diag B, 0))      std_errors.py:183-210
+    CUDA_CHECK(cudaMemcpyAsync(V.p, Binv, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    k_scale_se<<<1, 256, 0, s>>>(V, k, 1.0, stats, 2, (double)df_resid, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    return;
+  }
+  if (vcov_kind == LFE_VCOV_HC1) {
+    // meat_ij = sum w x_i x_j r^2 ; V = B meat B * n/df      std_errors.py:217-282
+    gram_core(h, xc.data(), k, n, weights, resid, 0, meat, s);
+    if (h->world > 1) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
+    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+    KERNEL_CHECK();
+    k_scale_se<<<1, 256, 0, s>>>(V, k, (double)n_obs / (double)df_resid, nullptr, 0, 1.0, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    return;
+  }
+  cluster_sandwich(h, cl_codes, n_cl_groups, W, xc.data(), k, resid, weights, n, Binv, ssc, n_obs, df_resid, V, tmp,
+                   meat, se_out, vcov_out, n_clusters_out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// YOCO standard errors on the compressed table   (compress.py:754-810, 854-1042, 1118-1137)
+// ---------------------------------------------------------------------------------------------
+// The reference solves the full dummy-variable WLS and sandwiches with rows of (M'WM)^-1.  By
+// Frisch-Waugh-Lovell the x-block of that inverse is B = (X~' W X~)^-1 and (M'WM)^-1[x,:] M' = B X~',
+// with X~ the W-weighted FE-demeaned regressors, so every estimator below is identical to the
+// reference's without ever materialising the FE dummies:
+//   e_g   = y~_g - x~_g'beta           (== mean_y_g - yhat_g)
+//   rss_g = sum_y_sq - 2 yhat sum_y + n yhat^2 ,  e0_g = sum_y - n yhat
+//   iid : rss/df * B ; hc1 : n/df * B (X~' diag(rss_g) X~) B ; cluster : scores = sum_g x~_g e0_g
+__global__ void __launch_bounds__(256) k_yoco_rows(const double* __restrict__ yt, XCols X, int k,
+                                                   const double* __restrict__ beta, const double* __restrict__ nn,
+                                                   const double* __restrict__ sum_y, const double* __restrict__ sum_y_sq,
+                                                   int64_t G, double* __restrict__ rss_g, double* __restrict__ e0_g,
+                                                   double* __restrict__ rss_total) {
+  double local = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x) {
+    double e = yt[g];
+    for (int j = 0; j < k; ++j) e = fma(-beta[j], X.col[j][g], e);
+    double n = nn[g], sy = sum_y[g];
+    double yhat = sy / n - e;
+    double rg = sum_y_sq[g] - 2.0 * yhat * sy + n * (yhat * yhat);
+    rss_g[g] = rg;
+    e0_g[g] = sy - n * yhat;
+    local += rg;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(rss_total, local);
+}
+
+void yoco_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t G, const double* beta, const double* Binv,
+                    const double* nn, const double* sum_y, const double* sum_y_sq, int vcov_kind,
+                    const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W, int ssc, int64_t n_obs,
+                    int64_t df_resid, double* se_out, double* vcov_out, double* rss_out, int64_t* n_clusters_out,
+                    cudaStream_t s) {
+  PhaseTimer t(h, s, 11);
+  LFE_REQUIRE(k >= 1 && k <= RV_MAXK, "lfe_yoco_vcov: k=%d out of range", k);
+  LFE_REQUIRE(G >= 1, "lfe_yoco_vcov: empty table");
+  LFE_REQUIRE(vcov_kind >= 0 && vcov_kind <= 2, "lfe_yoco_vcov: unknown vcov kind %d", vcov_kind);
+  if (vcov_kind == LFE_VCOV_CLUSTER) LFE_REQUIRE(W >= 1 && W <= LFE_MAX_CLUSTER_WAYS, "lfe_yoco_vcov: cluster codes required");
+  XCols X;
+  std::vector<const double*> xc(k);
+  for (int j = 0; j < k; ++j) X.col[j] = xc[j] = cols[1 + j];
+  DevBuf<double> rss_g(G, s), e0_g(G, s), rss_loc(1, s);
+  double* rss = rss_out ? rss_out : rss_loc.p;
+  CUDA_CHECK(cudaMemsetAsync(rss, 0, sizeof(double), s));
+  k_yoco_rows<<<launch_blocks(h, ceil_div64(G, 256), 4), 256, 0, s>>>(cols[0], X, k, beta, nn, sum_y, sum_y_sq, G, rss_g,
+                                                                      e0_g, rss);
+  KERNEL_CHECK();
+  h->n_launches += 1;
+  DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
+  V.zero();
+  if (vcov_kind == LFE_VCOV_IID) {
+    CUDA_CHECK(cudaMemcpyAsync(V.p, Binv, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    k_scale_se<<<1, 256, 0, s>>>(V, k, 1.0, rss, 0, (double)df_resid, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    return;
+  }
+  if (vcov_kind == LFE_VCOV_HC1) {
+    gram_core(h, xc.data(), k, G, rss_g, nullptr, 0, meat, s);
+    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+    KERNEL_CHECK();
+    k_scale_se<<<1, 256, 0, s>>>(V, k, (double)n_obs / (double)df_resid, nullptr, 0, 1.0, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    return;
+  }
+  cluster_sandwich(h, cl_codes, n_cl_groups, W, xc.data(), k, e0_g, nullptr, G, Binv, ssc, n_obs, df_resid, V, tmp, meat,
+                   se_out, vcov_out, n_clusters_out, s);
+}

@@ -1,0 +1,320 @@
+"""Thin host wrapper: PyTorch tensors as device buffers, every compute call goes to liblfe.so.
+
+PyTorch is plumbing here (allocation, streams, H2D/D2H copies); no arithmetic of the hot path is
+done with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+
+_TORCH_TO_LFE = {
+    torch.int32: capi.LFE_I32, torch.int64: capi.LFE_I64, torch.float64: capi.LFE_F64, torch.uint8: capi.LFE_U8,
+}
+if hasattr(torch, "uint32"):
+    _TORCH_TO_LFE[torch.uint32] = capi.LFE_U32
+if hasattr(torch, "uint64"):
+    _TORCH_TO_LFE[torch.uint64] = capi.LFE_U64
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("leanfe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+class Engine:
+    """One liblfe handle on one CUDA device."""
+
+    def __init__(self, device: int | None = None, profiling: bool = False):
+        _require_cuda()
+        self.lib = capi.load_library()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        capi.check(self.lib.lfe_create(self.device_index, C.byref(h)))
+        self.h = h
+        self.world, self.rank = 1, 0
+        if profiling:
+            self.set_profiling(True)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lfe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def zeros(self, n, dtype):
+        return torch.zeros(int(n), dtype=dtype, device=self.device)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _check_dev(self, *ts):
+        for t in ts:
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
+                raise ValueError("expected contiguous CUDA tensors")
+
+    # -- profiling -----------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        capi.check(self.lib.lfe_set_profiling(self.h, 1 if on else 0))
+
+    def reset_timers(self):
+        capi.check(self.lib.lfe_reset_timers(self.h))
+
+    def timers(self) -> dict:
+        out = (C.c_double * capi.N_TIMERS)()
+        capi.check(self.lib.lfe_get_timers(self.h, out))
+        return {capi.TIMER_NAMES[i]: out[i] for i in range(14)}
+
+    def counters(self) -> dict:
+        out = (C.c_int64 * 4)()
+        capi.check(self.lib.lfe_get_counters(self.h, out))
+        return {"launches": out[0], "sweep_launches": out[1]}
+
+    # -- (1) group codes ----------------------------------------------------------------------
+    def factorize(self, keys: torch.Tensor, order: int = capi.ORDER_SORTED, want_uniques: bool = False,
+                  uniques_cap: int | None = None):
+        """-> (codes int32, n_groups, uniques or None)"""
+        self._check_dev(keys)
+        if keys.dtype not in _TORCH_TO_LFE:
+            raise TypeError(f"unsupported key dtype {keys.dtype}")
+        n = keys.numel()
+        codes = self.empty(n, torch.int32)
+        G = C.c_int64(0)
+        uniq = None
+        cap = 0
+        if want_uniques:
+            cap = n if uniques_cap is None else min(n, int(uniques_cap))
+            uniq = self.empty(cap, keys.dtype)
+        rc = self.lib.lfe_factorize(self.h, self._p(keys), _TORCH_TO_LFE[keys.dtype], n, order, self._p(codes),
+                                    C.byref(G), self._p(uniq), cap, self.stream)
+        if rc == capi.ERR_CAPACITY and want_uniques and cap < n:
+            return self.factorize(keys, order, True, n)
+        capi.check(rc)
+        return codes, int(G.value), (uniq[: G.value] if uniq is not None else None)
+
+    def group_counts(self, codes: torch.Tensor, n_groups: int) -> torch.Tensor:
+        self._check_dev(codes)
+        out = self.empty(n_groups, torch.int32)
+        capi.check(self.lib.lfe_group_counts(self.h, self._p(codes), codes.numel(), n_groups, self._p(out), self.stream))
+        return out
+
+    def singleton_mask(self, codes: list[torch.Tensor], n_groups: list[int]):
+        """-> (keep uint8, n_keep, fe_dims)"""
+        self._check_dev(*codes)
+        n = codes[0].numel()
+        keep = self.empty(n, torch.uint8)
+        n_keep = C.c_int64(0)
+        dims = (C.c_int64 * len(codes))()
+        capi.check(self.lib.lfe_singleton_mask(self.h, capi.ptr_array([c.data_ptr() for c in codes]),
+                                               capi.i64_array(n_groups), len(codes), n, self._p(keep),
+                                               C.byref(n_keep), dims, self.stream))
+        return keep, int(n_keep.value), tuple(int(d) for d in dims)
+
+    def compact(self, keep: torch.Tensor, n_keep: int, f64: list[torch.Tensor], i32: list[torch.Tensor]):
+        self._check_dev(keep, *f64, *i32)
+        f_out = [self.empty(n_keep, torch.float64) for _ in f64]
+        i_out = [self.empty(n_keep, torch.int32) for _ in i32]
+        capi.check(self.lib.lfe_compact(self.h, self._p(keep), keep.numel(),
+                                        capi.ptr_array([t.data_ptr() for t in f64]),
+                                        capi.ptr_array([t.data_ptr() for t in f_out]), len(f64),
+                                        capi.ptr_array([t.data_ptr() for t in i32]),
+                                        capi.ptr_array([t.data_ptr() for t in i_out]), len(i32), self.stream))
+        return f_out, i_out
+
+    def sort_rows(self, codes: torch.Tensor, n_groups: int):
+        """-> (perm int32, already_sorted)"""
+        self._check_dev(codes)
+        perm = self.empty(codes.numel(), torch.int32)
+        flag = C.c_int(0)
+        capi.check(self.lib.lfe_sort_rows(self.h, self._p(codes), codes.numel(), n_groups, self._p(perm),
+                                          C.byref(flag), self.stream))
+        return perm, bool(flag.value)
+
+    def gather(self, perm: torch.Tensor, f64: list[torch.Tensor], i32: list[torch.Tensor]):
+        self._check_dev(perm, *f64, *i32)
+        n = perm.numel()
+        f_out = [self.empty(n, torch.float64) for _ in f64]
+        i_out = [self.empty(n, torch.int32) for _ in i32]
+        capi.check(self.lib.lfe_gather(self.h, self._p(perm), n, capi.ptr_array([t.data_ptr() for t in f64]),
+                                       capi.ptr_array([t.data_ptr() for t in f_out]), len(f64),
+                                       capi.ptr_array([t.data_ptr() for t in i32]),
+                                       capi.ptr_array([t.data_ptr() for t in i_out]), len(i32), self.stream))
+        return f_out, i_out
+
+    # -- (2) demean ---------------------------------------------------------------------------
+    def demean(self, cols: list[torch.Tensor], codes: list[torch.Tensor], n_groups: list[int], fe_order: list[int],
+               weights: torch.Tensor | None = None, tol: float = 1e-6, max_iter: int = 50, min_iter: int = 3,
+               local_fe: int = -1, strict_check: bool = False):
+        """In place.  -> (iterations, max_mean, converged)"""
+        self._check_dev(*cols, *codes, weights)
+        n = cols[0].numel()
+        for t in cols:
+            if t.dtype != torch.float64 or t.numel() != n:
+                raise ValueError("demean columns must be float64 of equal length")
+        for t in codes:
+            if t.dtype != torch.int32 or t.numel() != n:
+                raise ValueError("codes must be int32 of the same length as the columns")
+        it, mm, cv = C.c_int(0), C.c_double(0.0), C.c_int(0)
+        capi.check(self.lib.lfe_demean(self.h, capi.ptr_array([t.data_ptr() for t in cols]), len(cols),
+                                       capi.ptr_array([t.data_ptr() for t in codes]), capi.i64_array(n_groups),
+                                       capi.i32_array(fe_order), len(codes), n, self._p(weights), float(tol),
+                                       int(max_iter), int(min_iter), int(local_fe), 1 if strict_check else 0,
+                                       C.byref(it), C.byref(mm),
+                                       C.byref(cv), self.stream))
+        return int(it.value), float(mm.value), bool(cv.value)
+
+    # -- (4) gram / solve ---------------------------------------------------------------------
+    def gram(self, cols: list[torch.Tensor], weights: torch.Tensor | None = None, add_intercept: bool = True):
+        self._check_dev(*cols, weights)
+        P = len(cols) + (1 if add_intercept else 0)
+        n = cols[0].numel() if cols else 0
+        out = self.empty(P * P, torch.float64)
+        capi.check(self.lib.lfe_gram(self.h, capi.ptr_array([t.data_ptr() for t in cols]), len(cols), n,
+                                     self._p(weights), 1 if add_intercept else 0, self._p(out), self.stream))
+        return out.view(P, P)
+
+    def solve_spd(self, A: torch.Tensor, b: torch.Tensor):
+        """-> (beta, Ainv, used_fallback)"""
+        A = A.contiguous()
+        b = b.contiguous()
+        self._check_dev(A, b)
+        p = b.numel()
+        beta = self.empty(p, torch.float64)
+        Ainv = self.empty(p * p, torch.float64)
+        fb = C.c_int(0)
+        capi.check(self.lib.lfe_solve_spd(self.h, self._p(A), self._p(b), p, self._p(beta), self._p(Ainv),
+                                          C.byref(fb), self.stream))
+        return beta, Ainv.view(p, p), bool(fb.value)
+
+    # -- (5) residuals + vcov ----------------------------------------------------------------
+    def resid_vcov(self, cols: list[torch.Tensor], beta_full: torch.Tensor, Binv: torch.Tensor, vcov_kind: int,
+                   cl_codes: list[torch.Tensor] | None, n_cl_groups: list[int] | None,
+                   weights: torch.Tensor | None, ssc: bool, n_obs: int, df_resid: int, want_resid: bool = False):
+        """-> dict(se, vcov, stats=[rss, tss, sum_w_r2], n_clusters, resid)"""
+        cl_codes = cl_codes or []
+        n_cl_groups = n_cl_groups or []
+        self._check_dev(*cols, beta_full, weights, *cl_codes)
+        k = len(cols) - 1
+        n = cols[0].numel()
+        Binv = Binv.contiguous() if Binv is not None else None
+        se = self.empty(max(k, 1), torch.float64)
+        V = self.empty(max(k * k, 1), torch.float64)
+        stats = self.empty(4, torch.float64)
+        resid = self.empty(n, torch.float64) if want_resid else None
+        ncl = (C.c_int64 * max(len(cl_codes), 1))()
+        capi.check(self.lib.lfe_resid_vcov(self.h, capi.ptr_array([t.data_ptr() for t in cols]), k, n,
+                                           self._p(beta_full), self._p(Binv), vcov_kind,
+                                           capi.ptr_array([t.data_ptr() for t in cl_codes]),
+                                           capi.i64_array(n_cl_groups), len(cl_codes), self._p(weights),
+                                           1 if ssc else 0, int(n_obs), int(df_resid), self._p(se), self._p(V),
+                                           self._p(stats), self._p(resid), ncl, self.stream))
+        return dict(se=se[:k], vcov=V[: k * k].view(k, k), stats=stats,
+                    n_clusters=[int(ncl[i]) for i in range(len(cl_codes))], resid=resid)
+
+    def yoco_vcov(self, cols: list[torch.Tensor], beta: torch.Tensor, Binv: torch.Tensor, nn, sum_y, sum_y_sq,
+                  vcov_kind: int, cl_codes, n_cl_groups, ssc: bool, n_obs: int, df_resid: int):
+        """-> dict(se, vcov, rss, n_clusters)"""
+        cl_codes = cl_codes or []
+        n_cl_groups = n_cl_groups or []
+        Binv = Binv.contiguous()
+        self._check_dev(*cols, beta, Binv, nn, sum_y, sum_y_sq, *cl_codes)
+        k = len(cols) - 1
+        se = self.empty(k, torch.float64)
+        V = self.empty(k * k, torch.float64)
+        rss = self.zeros(1, torch.float64)
+        ncl = (C.c_int64 * max(len(cl_codes), 1))()
+        capi.check(self.lib.lfe_yoco_vcov(self.h, capi.ptr_array([t.data_ptr() for t in cols]), k, cols[0].numel(),
+                                          self._p(beta), self._p(Binv), self._p(nn), self._p(sum_y),
+                                          self._p(sum_y_sq), vcov_kind,
+                                          capi.ptr_array([t.data_ptr() for t in cl_codes]),
+                                          capi.i64_array(n_cl_groups), len(cl_codes), 1 if ssc else 0, int(n_obs),
+                                          int(df_resid), self._p(se), self._p(V), self._p(rss), ncl, self.stream))
+        return dict(se=se, vcov=V.view(k, k), rss=rss, n_clusters=[int(ncl[i]) for i in range(len(cl_codes))])
+
+    # -- (3) compress -------------------------------------------------------------------------
+    def compress(self, key_codes: list[torch.Tensor], n_groups: list[int], y: torch.Tensor | None,
+                 weights: torch.Tensor | None = None, out_cap: int | None = None, count_only: bool = False):
+        """-> dict(n_compressed, key_codes, n, cnt, sum_y, sum_y_sq)"""
+        self._check_dev(*key_codes, y, weights)
+        n = key_codes[0].numel() if key_codes else (y.numel() if y is not None else 0)
+        K = len(key_codes)
+        G = C.c_int64(0)
+        if count_only:
+            capi.check(self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]),
+                                             capi.i64_array(n_groups), K, None, None, n, 0, None, None, None, None,
+                                             None, C.byref(G), self.stream))
+            return dict(n_compressed=int(G.value))
+        space = 1
+        for g in n_groups:
+            space *= int(g)
+        cap = int(min(n, space if out_cap is None else out_cap)) if K else 1
+        while True:
+            kout = [self.empty(cap, torch.int32) for _ in range(K)]
+            nn, sy, syy = (self.empty(cap, torch.float64) for _ in range(3))
+            cnt = self.empty(cap, torch.int32)
+            rc = self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]),
+                                       capi.i64_array(n_groups), K, self._p(y), self._p(weights), n, cap,
+                                       capi.ptr_array([t.data_ptr() for t in kout]), self._p(nn), self._p(cnt),
+                                       self._p(sy), self._p(syy), C.byref(G), self.stream)
+            if rc == capi.ERR_CAPACITY and cap < n:
+                cap = n
+                continue
+            capi.check(rc)
+            break
+        g = int(G.value)
+        return dict(n_compressed=g, key_codes=[t[:g] for t in kout], n=nn[:g], cnt=cnt[:g], sum_y=sy[:g],
+                    sum_y_sq=syy[:g])
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_init_from_torch(self):
+        """Attach an NCCL communicator spanning the default torch.distributed group."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world == 1:
+            return
+        uid = (C.c_ubyte * 128)()
+        if rank == 0:
+            capi.check(self.lib.lfe_comm_unique_id(uid))
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        buf = (C.c_ubyte * 128)(*t.cpu().tolist())
+        capi.check(self.lib.lfe_comm_init(self.h, buf, rank, world))
+        self.world, self.rank = world, rank
+
+    def allreduce(self, t: torch.Tensor):
+        capi.check(self.lib.lfe_allreduce_f64(self.h, self._p(t), t.numel(), self.stream))
+        return t
+
+
+_ENGINES: dict[int, Engine] = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    _require_cuda()
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _ENGINES:
+        _ENGINES[idx] = Engine(idx)
+    return _ENGINES[idx]
+
+
+def to_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()

@@ -1,0 +1,143 @@
+"""Input adapters and column expansion (the reference's front end, polars_impl.py:311-365).
+
+Host-side, metadata-level work stays in Python: resolving columns from a dict / pandas / pyarrow /
+parquet / Polars frame, dictionary-encoding string ids (the reference's ``_cats_to_int``,
+polars_impl.py:118-139, is also a host-side hash), naming dummy columns.  Everything per-row runs on
+the device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from .engine import Engine
+
+
+class Frame:
+    """Uniform, lazy column access over the accepted ``data`` kinds."""
+
+    def __init__(self, data, needed: list[str]):
+        self._cols = {}
+        self._getter = None
+        if data is None:
+            raise ValueError("A dataset must be provided")
+        if isinstance(data, str):
+            import pyarrow.parquet as pq
+            table = pq.read_table(data, columns=needed)
+            self._from_arrow(table)
+        elif isinstance(data, dict):
+            self._getter = data.__getitem__
+            self._names = list(data.keys())
+        else:
+            mod = type(data).__module__.split(".")[0]
+            if mod == "pandas":
+                self._getter = lambda c: data[c].to_numpy()
+                self._names = list(data.columns)
+            elif mod == "pyarrow":
+                self._from_arrow(data.select([c for c in needed if c in data.column_names]))
+            elif mod == "polars":
+                lf = data.lazy() if hasattr(data, "lazy") else data
+                self._from_arrow(lf.select(needed).collect().to_arrow())
+            else:
+                raise TypeError(f"unsupported data type {type(data)!r}: pass a dict of arrays/tensors, a pandas "
+                                "DataFrame, a pyarrow Table, a Polars frame or a parquet path")
+        missing = [c for c in needed if c not in self._names]
+        if missing:
+            raise KeyError(f"columns not found in data: {missing}")
+
+    def _from_arrow(self, table):
+        self._names = list(table.column_names)
+        self._getter = lambda c: _arrow_to_numpy(table.column(c))
+
+    def column(self, name: str):
+        if name not in self._cols:
+            self._cols[name] = self._getter(name)
+        return self._cols[name]
+
+
+def _arrow_to_numpy(chunked):
+    import pyarrow as pa
+    arr = chunked.combine_chunks() if hasattr(chunked, "combine_chunks") else chunked
+    if arr.null_count:
+        raise ValueError("null values are not supported in model columns (the reference's Polars path never filters them)")
+    if pa.types.is_dictionary(arr.type):
+        arr = arr.dictionary_decode()
+    if pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type):
+        return np.asarray(arr.to_pylist(), dtype=object)
+    return arr.to_numpy(zero_copy_only=False)
+
+
+@dataclass
+class KeyColumn:
+    """A group-key column on the device: dense int32 codes + cardinality (+ labels when needed)."""
+    codes: torch.Tensor
+    n_groups: int
+    labels: list | None = None     # python scalars in code order (sorted ascending)
+
+
+def _is_stringlike(col) -> bool:
+    return isinstance(col, np.ndarray) and col.dtype.kind in ("O", "U", "S")
+
+
+def to_device_f64(eng: Engine, col) -> torch.Tensor:
+    if isinstance(col, torch.Tensor):
+        t = col.to(eng.device, non_blocking=True)
+    else:
+        a = np.asarray(col)
+        if a.dtype.kind in ("O", "U", "S"):
+            raise TypeError("string column used as a numeric regressor")
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(eng.device, non_blocking=True)
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def to_device_key(eng: Engine, col, want_labels: bool = False) -> KeyColumn:
+    """Factorise a key column to sorted-rank codes (== np.unique(..., return_inverse=True))."""
+    if _is_stringlike(col):
+        # strings stay on the host: dictionary-encode there, ship int32 codes (SURVEY 7 'hard parts')
+        uniq, inv = np.unique(col, return_inverse=True)
+        codes = torch.from_numpy(inv.reshape(-1).astype(np.int32)).to(eng.device, non_blocking=True)
+        return KeyColumn(codes, int(uniq.shape[0]), uniq.tolist() if want_labels else None)
+    if isinstance(col, torch.Tensor):
+        t = col.to(eng.device, non_blocking=True).contiguous()
+    else:
+        a = np.asarray(col)
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        elif a.dtype in (np.int8, np.int16):
+            a = a.astype(np.int32)
+        elif a.dtype == np.uint16:
+            a = a.astype(np.int32)
+        elif a.dtype == np.float32:
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(eng.device, non_blocking=True)
+    if t.dtype in (torch.int8, torch.int16):
+        t = t.to(torch.int32)
+    elif t.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        t = t.to(torch.float64)
+    elif t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    codes, G, uniq = eng.factorize(t, capi.ORDER_SORTED, want_uniques=want_labels, uniques_cap=1 << 16)
+    labels = uniq.cpu().tolist() if want_labels else None
+    return KeyColumn(codes, G, labels)
+
+
+def resolve_reference(labels: list, ref, var: str):
+    """Reference level of ``i(var, ref=...)``: first sorted level by default (polars_impl.py:44-55)."""
+    if ref is None:
+        return labels[0]
+    cand = ref
+    if labels and not isinstance(labels[0], type(ref)):
+        try:
+            cand = type(labels[0])(ref)
+        except (ValueError, TypeError):
+            pass
+    if cand not in labels:
+        raise ValueError(f"Reference category '{ref}' not found in {var}. Available: {labels}")
+    return cand

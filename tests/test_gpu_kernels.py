@@ -1,0 +1,326 @@
+"""GPU parity tests of each C-ABI entry point (through leanfe_b200.engine -> liblfe.so) against the oracle.
+
+Bit-exact for integer / index work (codes, counts, permutations, YOCO keys); fp64 tolerances are written
+beside each assertion.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_numpy as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from leanfe_b200.engine import get_engine
+    return get_engine(0)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) factorisation: bit-exact with np.unique / first-appearance
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["dense_i64", "shifted_i64", "negative_i32", "huge_range_i64", "u8", "single", "all_distinct"])
+def test_factorize_sorted_bit_exact(eng, case):
+    rng = np.random.default_rng(1)
+    n = 200_003
+    v = {
+        "dense_i64": rng.integers(0, 5000, n),
+        "shifted_i64": rng.integers(0, 700, n) * 7 + 12345,
+        "negative_i32": rng.integers(-3000, 3000, n).astype(np.int32),
+        "huge_range_i64": rng.choice(rng.integers(-2**62, 2**62, 4000), n),
+        "u8": rng.integers(0, 3, n).astype(np.uint8),
+        "single": np.full(n, 42, dtype=np.int64),
+        "all_distinct": rng.permutation(n).astype(np.int64) * 1_000_003,
+    }[case]
+    codes, G, uniq = eng.factorize(dev(v), want_uniques=True)
+    exp_codes, exp_uniq, _ = O.codes_sorted(v)
+    assert G == len(exp_uniq)
+    assert codes.dtype == torch.int32
+    np.testing.assert_array_equal(codes.cpu().numpy(), exp_codes)
+    np.testing.assert_array_equal(uniq.cpu().numpy(), exp_uniq)
+    cnt = eng.group_counts(codes, G)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), np.bincount(exp_codes, minlength=G))
+
+
+def test_factorize_float_keys_canonical(eng):
+    rng = np.random.default_rng(2)
+    v = rng.choice(np.array([0.0, -0.0, 1.5, -2.25, np.nan, np.inf, -np.inf, 1e-300, -1e-300]), 50_000)
+    v[::7] = np.float64("nan")
+    codes, G, uniq = eng.factorize(dev(v), want_uniques=True)
+    exp_codes, exp_uniq, _ = O.codes_sorted(v)
+    assert G == len(exp_uniq)
+    np.testing.assert_array_equal(codes.cpu().numpy(), exp_codes)
+    np.testing.assert_array_equal(uniq.cpu().numpy(), exp_uniq)          # NaN == NaN positionally
+    assert not np.signbit(uniq.cpu().numpy()[exp_uniq == 0.0]).any()     # -0.0 was canonicalised to +0.0
+
+
+def test_factorize_first_appearance(eng):
+    rng = np.random.default_rng(3)
+    v = rng.integers(0, 3000, 100_000) * 11 - 500
+    codes, G, uniq = eng.factorize(dev(v), order=1, want_uniques=True)
+    exp_codes, exp_uniq = O.codes_first_appearance(v)
+    assert G == len(exp_uniq)
+    np.testing.assert_array_equal(codes.cpu().numpy(), exp_codes)
+    np.testing.assert_array_equal(uniq.cpu().numpy(), exp_uniq)
+
+
+def test_factorize_empty(eng):
+    codes, G, _ = eng.factorize(torch.empty(0, dtype=torch.int64, device="cuda"))
+    assert G == 0 and codes.numel() == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# singleton mask / compaction / ordering
+# ------------------------------------------------------------------------------------------------
+def test_singleton_mask_compact_sort(eng):
+    rng = np.random.default_rng(4)
+    n = 150_001
+    a = rng.integers(0, 60_000, n).astype(np.int32)      # many singletons
+    b = rng.integers(0, 40, n).astype(np.int32)
+    x = rng.normal(size=n)
+    keep, n_keep, dims = eng.singleton_mask([dev(a), dev(b)], [60_000, 40])
+    exp = O.singleton_keep_mask([a, b])
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), exp)
+    assert n_keep == int(exp.sum()) and n_keep < n
+    assert dims == (np.unique(a[exp]).size, np.unique(b[exp]).size)
+    (xo,), (ao, bo) = eng.compact(keep, n_keep, [dev(x)], [dev(a), dev(b)])
+    np.testing.assert_array_equal(xo.cpu().numpy(), x[exp])
+    np.testing.assert_array_equal(ao.cpu().numpy(), a[exp])
+    np.testing.assert_array_equal(bo.cpu().numpy(), b[exp])
+    perm, was_sorted = eng.sort_rows(ao, 60_000)
+    assert not was_sorted
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(a[exp], kind="stable"))    # stable => bit-exact
+    (xs,), (as_,) = eng.gather(perm, [xo], [ao])
+    np.testing.assert_array_equal(as_.cpu().numpy(), np.sort(a[exp], kind="stable"))
+    np.testing.assert_array_equal(xs.cpu().numpy(), x[exp][np.argsort(a[exp], kind="stable")])
+    perm2, was_sorted2 = eng.sort_rows(as_, 60_000)
+    assert was_sorted2
+    np.testing.assert_array_equal(perm2.cpu().numpy(), np.arange(n_keep))
+
+
+@pytest.mark.parametrize("G", [1, 2, 255, 256, 257, 70_000, 3_000_000])
+def test_sort_rows_radix_widths(eng, G):
+    rng = np.random.default_rng(G)
+    n = 300_007
+    a = rng.integers(0, G, n).astype(np.int32)
+    perm, _ = eng.sort_rows(dev(a), G)
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(a, kind="stable"))
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) demean
+# ------------------------------------------------------------------------------------------------
+def _panel(rng, n, Gs, C):
+    codes = [rng.integers(0, g, n).astype(np.int32) for g in Gs]
+    cols = [rng.normal(size=n) + sum(rng.normal(size=g)[c] for g, c in zip(Gs, codes)) for _ in range(C)]
+    return cols, codes
+
+
+@pytest.mark.parametrize("Gs,C,weighted", [((3000, 40), 3, False), ((3000, 40), 6, True), ((500, 200, 12), 2, False),
+                                           ((50,), 4, False), ((2000, 300), 11, False), ((64, 8, 5, 3), 1, True)])
+def test_demean_matches_oracle(eng, Gs, C, weighted):
+    rng = np.random.default_rng(sum(Gs) + C)
+    n = 120_000
+    cols, codes = _panel(rng, n, Gs, C)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    order = O.fe_order(list(Gs))
+    max_iter = 7
+    exp_cols, exp_it, exp_mm = O.alt_proj(cols, codes, order, 0.0, max_iter, w)         # fixed sweep count
+    d_cols = [dev(c) for c in cols]
+    it, mm, conv = eng.demean(d_cols, [dev(c) for c in codes], list(Gs), order, dev(w) if weighted else None,
+                              0.0, max_iter, 3)
+    assert it == exp_it == max_iter and not conv
+    for got, exp in zip(d_cols, exp_cols):
+        # same Gauss-Seidel iterates; only fp64 summation order differs (values are O(1))
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=2e-12)
+    assert mm == pytest.approx(exp_mm, rel=1e-6, abs=1e-14)
+
+
+def test_demean_convergence_and_iteration_parity(eng):
+    rng = np.random.default_rng(11)
+    n = 400_000
+    cols, codes = _panel(rng, n, (20_000, 100), 3)
+    order = [1, 0]
+    exp_cols, exp_it, exp_mm = O.alt_proj(cols, codes, order, 1e-6, 50)
+    d_cols = [dev(c) for c in cols]
+    it, mm, conv = eng.demean(d_cols, [dev(c) for c in codes], [20_000, 100], order, None, 1e-6, 50, 3)
+    assert conv and it == exp_it and 3 <= it < 10
+    assert mm < 1e-6 and mm == pytest.approx(exp_mm, rel=1e-5, abs=1e-13)
+    for got, exp in zip(d_cols, exp_cols):
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=1e-12)
+    # idempotence: demeaning demeaned columns changes nothing beyond the tolerance
+    before = [c.clone() for c in d_cols]
+    eng.demean(d_cols, [dev(c) for c in codes], [20_000, 100], order, None, 1e-6, 50, 3)
+    for a, b in zip(before, d_cols):
+        assert float((a - b).abs().max()) < 5e-6
+
+
+def test_demean_presorted_and_unsorted_agree(eng):
+    rng = np.random.default_rng(12)
+    n = 200_000
+    cols, codes = _panel(rng, n, (9000, 30), 2)
+    p = np.argsort(codes[0], kind="stable")
+    a = [dev(c) for c in cols]
+    b = [dev(c[p]) for c in cols]
+    eng.demean(a, [dev(c) for c in codes], [9000, 30], [1, 0], None, 1e-8, 50, 3)
+    eng.demean(b, [dev(c[p]) for c in codes], [9000, 30], [1, 0], None, 1e-8, 50, 3)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x.cpu().numpy()[p], y.cpu().numpy(), rtol=0, atol=1e-12)
+
+
+def test_demean_single_fe_within_transform(eng):
+    rng = np.random.default_rng(13)
+    n = 100_000
+    cols, codes = _panel(rng, n, (777,), 3)
+    d_cols = [dev(c) for c in cols]
+    it, _, _ = eng.demean(d_cols, [dev(codes[0])], [777], [0], None, 1e-6, 1, 2)
+    assert it == 1
+    for got, c in zip(d_cols, cols):
+        exp = c - (np.bincount(codes[0], weights=c, minlength=777) / np.bincount(codes[0], minlength=777))[codes[0]]
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=1e-12)
+
+
+def test_demean_empty_groups_allowed(eng):
+    rng = np.random.default_rng(14)
+    n = 50_000
+    cols, codes = _panel(rng, n, (300, 20), 2)
+    codes[0] = codes[0] * 3            # two thirds of the code space is empty
+    exp_cols, _, _ = O.alt_proj(cols, codes, [1, 0], 0.0, 5)
+    d_cols = [dev(c) for c in cols]
+    eng.demean(d_cols, [dev(c) for c in codes], [900, 20], [1, 0], None, 0.0, 5, 3)
+    for got, exp in zip(d_cols, exp_cols):
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=2e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# (4) gram + solve
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,weighted,intercept", [(1, False, True), (3, False, True), (7, True, True), (11, False, True),
+                                                  (12, False, False), (13, True, True), (24, False, True), (40, True, False)])
+def test_gram_matches_numpy(eng, C, weighted, intercept):
+    rng = np.random.default_rng(C)
+    n = 77_777
+    cols = [rng.normal(size=n) * (1 + j) + j for j in range(C)]
+    w = rng.uniform(0.1, 3.0, n) if weighted else None
+    Z = np.column_stack(([np.ones(n)] if intercept else []) + cols)
+    exp = Z.T @ (Z * (w[:, None] if weighted else 1.0))
+    got = eng.gram([dev(c) for c in cols], dev(w) if weighted else None, add_intercept=intercept).cpu().numpy()
+    np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-9)
+    np.testing.assert_array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("p", [1, 2, 6, 11, 33, 100])
+def test_solve_spd_matches_numpy(eng, p):
+    rng = np.random.default_rng(p)
+    M = rng.normal(size=(4 * p + 5, p))
+    A, b = M.T @ M, rng.normal(size=p)
+    beta, Ainv, fb = eng.solve_spd(dev(A), dev(b))
+    eb, eA, efb = O.solve_spd(A, b)
+    assert fb == efb is False
+    np.testing.assert_allclose(beta.cpu().numpy(), eb, rtol=1e-9)
+    np.testing.assert_allclose(Ainv.cpu().numpy(), eA, rtol=1e-8, atol=1e-12)
+
+
+def test_solve_spd_fallback_and_singular(eng):
+    from leanfe_b200._capi import LfeError
+    A = np.array([[2.0, 1.0], [1.0, -3.0]])          # symmetric, indefinite -> Cholesky fails -> LU path
+    b = np.array([1.0, 2.0])
+    beta, Ainv, fb = eng.solve_spd(dev(A), dev(b))
+    assert fb
+    np.testing.assert_allclose(beta.cpu().numpy(), np.linalg.solve(A, b), rtol=1e-12)
+    np.testing.assert_allclose(Ainv.cpu().numpy(), np.linalg.inv(A), rtol=1e-12)
+    with pytest.raises(LfeError, match="singular"):
+        eng.solve_spd(dev(np.zeros((2, 2))), dev(b))
+
+
+# ------------------------------------------------------------------------------------------------
+# (5) residuals + vcov
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,weighted", [(2, False), (5, True), (10, False)])
+def test_resid_vcov_all_kinds(eng, k, weighted):
+    rng = np.random.default_rng(100 + k)
+    n = 60_000
+    X = rng.normal(size=(n, k))
+    y = X @ rng.normal(size=k) + rng.normal(size=n) * (1 + 0.5 * np.abs(X[:, 0]))
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    cl1, cl2 = rng.integers(0, 500, n).astype(np.int32), rng.integers(0, 30, n).astype(np.int32)
+    reg = O.run_regression(y, X, w, n, absorbed_df=17)
+    cols = [dev(y)] + [dev(X[:, j]) for j in range(k)]
+    bf, B = dev(reg["beta_full"]), dev(reg["B"])
+    dw = dev(w) if weighted else None
+    args = (X, reg["B"], reg["resid"], w)
+    out = eng.resid_vcov(cols, bf, B, 0, None, None, dw, True, n, reg["df_resid"], want_resid=True)
+    np.testing.assert_allclose(out["resid"].cpu().numpy(), reg["resid"], rtol=0, atol=1e-12)
+    st = out["stats"].cpu().numpy()
+    assert st[0] == pytest.approx(reg["rss"], rel=1e-12) and st[1] == pytest.approx(reg["tss"], rel=1e-11)
+    np.testing.assert_allclose(out["se"].cpu().numpy(), O.se_iid(reg["B"], reg["resid"], w, reg["df_resid"]), rtol=1e-11)
+    out = eng.resid_vcov(cols, bf, B, 1, None, None, dw, True, n, reg["df_resid"])
+    np.testing.assert_allclose(out["se"].cpu().numpy(), O.se_hc1(*args, n, reg["df_resid"])[0], rtol=1e-10)
+    for ssc in (True, False):
+        out = eng.resid_vcov(cols, bf, B, 2, [dev(cl1)], [500], dw, ssc, n, reg["df_resid"])
+        se, G, V = O.se_cluster_oneway(*args, cl1, n, reg["df_resid"], ssc)
+        np.testing.assert_allclose(out["se"].cpu().numpy(), se, rtol=1e-10)
+        np.testing.assert_allclose(out["vcov"].cpu().numpy(), V, rtol=1e-9, atol=1e-18)
+        assert out["n_clusters"] == [G]
+        out = eng.resid_vcov(cols, bf, B, 2, [dev(cl1), dev(cl2)], [500, 30], dw, ssc, n, reg["df_resid"])
+        se, Gs, _ = O.se_cluster_multiway(*args, [cl1, cl2], n, reg["df_resid"], ssc)
+        np.testing.assert_allclose(out["se"].cpu().numpy(), se, rtol=1e-9)
+        assert tuple(out["n_clusters"]) == Gs
+    # sorted cluster codes take the segmented path: same answer
+    p = np.argsort(cl1, kind="stable")
+    cols_s = [dev(y[p])] + [dev(X[p, j]) for j in range(k)]
+    out = eng.resid_vcov(cols_s, bf, B, 2, [dev(cl1[p])], [500], dev(w[p]) if weighted else None, True, n, reg["df_resid"])
+    np.testing.assert_allclose(out["se"].cpu().numpy(), O.se_cluster_oneway(*args, cl1, n, reg["df_resid"], True)[0], rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) YOCO compression: keys and counts bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("weighted", [False, True])
+def test_compress_bit_exact_keys_and_counts(eng, weighted):
+    rng = np.random.default_rng(21)
+    n = 300_000
+    keys = [rng.integers(0, 2, n), rng.integers(0, 3, n), rng.integers(0, 50, n) * 3 - 7, rng.integers(0, 12, n)]
+    y = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    exp = O.compress(y, keys, w)
+    kc, Gs = [], []
+    for kcol in keys:
+        c, G, _ = eng.factorize(dev(kcol))
+        kc.append(c)
+        Gs.append(G)
+    got = eng.compress(kc, Gs, dev(y), dev(w) if weighted else None)
+    assert got["n_compressed"] == exp["n_compressed"]
+    for a, b in zip(got["key_codes"], exp["key_codes"]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)                                  # bit-exact, sorted order
+    cnt = np.bincount(np.unique(np.column_stack(exp["key_codes"]), axis=0, return_inverse=True)[1].reshape(-1)) * 0
+    if not weighted:
+        np.testing.assert_array_equal(got["cnt"].cpu().numpy(), exp["n"].astype(np.int64))  # bit-exact counts
+    np.testing.assert_allclose(got["n"].cpu().numpy(), exp["n"], rtol=1e-13)
+    np.testing.assert_allclose(got["sum_y"].cpu().numpy(), exp["sum_y"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), exp["sum_y_sq"], rtol=1e-11)
+    r = eng.compress(kc, Gs, None, count_only=True)
+    assert r["n_compressed"] == exp["n_compressed"]
+    # checksum of checksums: totals are preserved by the group-by
+    assert float(got["sum_y"].sum()) == pytest.approx(float((y * (w if weighted else 1.0)).sum()), rel=1e-9, abs=1e-8)
+    assert int(got["cnt"].sum()) == n
+
+
+def test_compress_known_answer_from_reference_docstring(eng):
+    # compress.py:318-323: 3 rows -> 2 groups
+    kc, Gs = [], []
+    for col in (np.array([1, 1, 2]), np.array([1, 1, 2])):
+        c, G, _ = eng.factorize(dev(col))
+        kc.append(c)
+        Gs.append(G)
+    got = eng.compress(kc, Gs, dev(np.array([1.0, 2.0, 3.0])))
+    assert got["n_compressed"] == 2
+    np.testing.assert_array_equal(got["cnt"].cpu().numpy(), [2, 1])
+    np.testing.assert_allclose(got["sum_y"].cpu().numpy(), [3.0, 3.0])
+    np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), [5.0, 9.0])
