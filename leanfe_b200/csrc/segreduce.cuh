@@ -53,11 +53,15 @@ __device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ
       for (int c = 0; c < NC; ++c) run[c] = v[e][c];
     }
   }
-  // inclusive segmented scan of the tail runs (equal keys are contiguous across lanes)
+  // inclusive segmented scan of the tail runs.  Segments are maximal runs of ADJACENT lanes with equal
+  // keys (head flags), so the result is exact for unsorted keys too (equal keys that are not adjacent
+  // simply end up in separate atomics).
+  const int prv = __shfl_up_sync(0xffffffffu, cur, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prv != cur);
+  const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    int ok = __shfl_up_sync(0xffffffffu, cur, d);
-    bool add = (lane >= d) && (ok == cur);
+    bool add = (lane - d >= seg_start);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       double t = shfl_up_d(run[c], d);
