@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- fit rows/s on BASELINE.json config 2 (50M rows, 5 regressors | unit(1M) + time(500),
+clustered by unit) and the demean-sweep roofline, with the reference algorithm timed on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+
+A "step" is one complete fit through the public API (`leanfe_b200.leanfe`): factorise the raw int64
+ids, singleton filter, order rows by unit, alternating projections to the reference's tolerance, Gram,
+Cholesky solve, cluster-robust sandwich.  `value` = rows/s with the inputs already resident in HBM;
+`e2e` = the same call on pinned HOST tensors (H2D inside the timed region, result read back).
+With N > 1 (torchrun) every rank owns a disjoint block of units (weak scaling: 50M rows per GPU); the
+time-FE tables, Gram and meat are all-reduced over NCCL inside liblfe.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_REG = 5
+N_TIME = 500
+ROWS_PER_UNIT = 50
+FORMULA = "y ~ x1 + x2 + x3 + x4 + x5 | unit + time"
+
+
+def make_panel(n_rows: int, seed: int, unit_offset: int = 0, out=None):
+    """unit ~ U{0..N/50}, time ~ U{0..500}, x_j ~ N(0,1) + 0.5 a_unit,
+    eps = s_unit * N(0,1) with s ~ U(0.5, 1.5), y = sum (1 + 0.1 j) x_j + a_unit + g_time + eps."""
+    rng = np.random.default_rng(seed)
+    G1 = max(n_rows // ROWS_PER_UNIT, 2)
+    unit = rng.integers(0, G1, n_rows)
+    tm = rng.integers(0, N_TIME, n_rows)
+    a, g, s = rng.normal(size=G1), rng.normal(size=N_TIME), rng.uniform(0.5, 1.5, G1)
+    au = a[unit]
+    d = {}
+    y = au + g[tm] + s[unit] * rng.normal(size=n_rows)
+    for j in range(1, K_REG + 1):
+        x = rng.normal(size=n_rows)
+        x += 0.5 * au
+        y += (1 + 0.1 * j) * x
+        d[f"x{j}"] = x
+    d["y"] = y
+    d["unit"] = unit + unit_offset
+    d["time"] = tm
+    return d, G1
+
+
+def sample_for_cpu(d: dict, G1: int, target_rows: int):
+    """Bounded sample of the same workload: all rows of the first units (keeps ~50 rows per unit, all 500 periods)."""
+    n = d["y"].shape[0]
+    if target_rows >= n:
+        return d, n
+    cut = int(G1 * target_rows / n)
+    base = int(d["unit"].min())
+    m = (d["unit"] - base) < cut
+    return {k: v[m] for k, v in d.items()}, int(m.sum())
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(d: dict, steps: int, warmup: int):
+    """Time the reference algorithm (OpenMP C port of polars_impl.py:468-537 + std_errors.py:289-347)."""
+    from oracle import ref_port as P
+    X = [d[f"x{j}"] for j in range(1, K_REG + 1)]
+    n = d["y"].shape[0]
+    times, res = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = P.fit(d["y"], X, [d["unit"], d["time"]], cluster=d["unit"], vcov="cluster", ssc=True, tol=1e-6, max_iter=50)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return n * len(times) / sum(times), P.threads(), res, float(np.mean(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=50_000_000, help="rows per GPU")
+    ap.add_argument("--cpu-rows", type=int, default=10_000_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = f"c2: {args.rows // 1_000_000}M rows/GPU, 5 regressors | unit({args.rows // ROWS_PER_UNIT}) + time(500), cluster(unit), ssc"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        d, G1 = make_panel(args.rows, 42)
+        ds, ns = sample_for_cpu(d, G1, args.cpu_rows)
+        del d
+        rate, cores, res, sec = cpu_reference_run(ds, args.steps, max(args.warmup, 1))
+        sample = f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the {args.rows}-row panel"
+        print(json.dumps({
+            "impl": "reference", "metric": "fit rows/s", "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample, "sweeps": res["iterations"]},
+            "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "OpenMP C restatement of the reference algorithm (Polars 1.36.1 not installable)"},
+            "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from leanfe_b200 import leanfe
+    from leanfe_b200.engine import get_engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = get_engine(local_rank)
+    if world > 1:
+        eng.comm_init_from_torch()
+
+    # ---- synthetic panel in pinned host memory (rank r owns units [r*G1, (r+1)*G1)) ---------------
+    n = args.rows
+    d, G1 = make_panel(n, 42 + rank, unit_offset=rank * max(n // ROWS_PER_UNIT, 2))
+    host = {}
+    for k_, v in d.items():
+        t = torch.empty(v.shape, dtype=torch.from_numpy(v[:1]).dtype, pin_memory=True)
+        t.numpy()[...] = v
+        host[k_] = t
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+    kw = dict(formula=FORMULA, vcov="cluster", cluster_cols=["unit"], strategy="alt_proj")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm ----------------------------------------------------------------------
+    resident = {k_: t.to(dev) for k_, t in host.items()}
+    res = None
+    for _ in range(args.warmup):
+        res = leanfe(resident, **kw)
+    eng.set_profiling(True)
+    eng.reset_timers()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = leanfe(resident, **kw)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    timers = eng.timers()
+    counters = eng.counters()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if sampler else None
+    del resident
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: pinned host buffers -> public API -> result on the host ------------------
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            leanfe(host, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2 = leanfe(host, **kw)
+            _ = float(r2.coefs["x1"])
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_rows = n * world
+    value = total_rows * args.steps / (ms / 1e3)
+    e2e = total_rows * args.steps / (e2e_ms / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+
+    # ---- roofline of the demean sweep (dominant iterative kernel k_proj) -----------------------------
+    C, F = K_REG + 1, 2
+    sweeps = res.iterations
+    sweep_ms = timers["demean_sweeps"] / args.steps / max(sweeps, 1)
+    # bytes the coefficient-space sweep must move: per projection the FE-sorted int32 key + the other FE's code,
+    # plus one read of S0 and one read-modify-write of alpha/acc per group row (SURVEY 8d 'read-only sweep' form)
+    G_unit, G_time = n // ROWS_PER_UNIT, N_TIME
+    own_bytes = F * n * 4 * F + 5 * 8 * C * (G_unit + G_time)
+    inplace_bytes = n * F * (16 * C + 8)                    # the reference's in-place formulation
+    roofline = {
+        "bound": "hbm", "kernel": "k_proj<6,false> + k_finalize (one sweep = 2 projections)",
+        "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak, "traffic": None,
+        "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
+        "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
+                               "frac": inplace_bytes / (sweep_ms / 1e3) / 1e9 / peak,
+                               "note": "SURVEY 8(d) figure N*F*(16C+8) for the reference's in-place sweeps; this "
+                                       "implementation iterates in FE-coefficient space and never re-reads the columns"},
+    }
+    phases = {k_: round(v / args.steps, 4) for k_, v in timers.items() if v > 0}
+
+    out = {
+        "metric": "fit rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "rows_total": total_rows, "sweeps": sweeps, "converged": bool(res.converged),
+                   "l2": "inputs (3.2 GB/GPU) exceed the 126 MB L2; no explicit flush", "tol": 1e-6,
+                   "parallelism": f"row-sharded by unit x{world}" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * (2 * K_REG + 3),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(counters["launches"]),
+        "clocks": clocks, "roofline": roofline, "phases_ms_per_step": phases,
+        "coefs": {k_: float(v) for k_, v in res.coefs.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ds, ns = sample_for_cpu(d, G1, args.cpu_rows)
+        rate, cores, pres, sec = cpu_reference_run(ds, 1, 1)
+        out["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port", "seconds": sec,
+                               "sample": f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the same panel",
+                               "sweeps": pres["iterations"]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

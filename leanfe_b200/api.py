@@ -213,20 +213,13 @@ def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, 
         owned = False
         if n_keep < y.numel():
             f_in = cols + ([w] if w is not None else [])
-            f_out, i_out = eng.compact(keep, n_keep, f_in, codes + cl_codes)
+            extra = [c for c in cl_codes if not any(c is f for f in codes)]     # a cluster column may be an FE
+            f_out, i_out = eng.compact(keep, n_keep, f_in, codes + extra)
             cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
-            codes, cl_codes = i_out[:F], i_out[F:]
+            new_of = {id(o): n_ for o, n_ in zip(codes + extra, i_out)}
+            codes, cl_codes = i_out[:F], [new_of[id(c)] for c in cl_codes]
             owned = True
-        # order rows by the highest-cardinality FE: its groups become contiguous segments
-        big = max(range(F), key=lambda j: Gs[j])
-        perm, is_sorted = eng.sort_rows(codes[big], Gs[big])
-        if not is_sorted:
-            f_in = cols + ([w] if w is not None else [])
-            f_out, i_out = eng.gather(perm, f_in, codes + cl_codes)
-            cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
-            codes, cl_codes = i_out[:F], i_out[F:]
-            owned = True
-        del perm
+        # rows are never permuted: lfe_demean sorts only the int32 code columns (one entry list per FE)
         if not owned:
             cols = [c.clone() for c in cols]          # lfe_demean works in place; never touch caller data
         order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)

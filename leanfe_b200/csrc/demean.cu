@@ -9,8 +9,10 @@
 //
 // with S0_j[g] = sum_{i in g} w_i c_i computed once.  In exact arithmetic this is the reference's
 // Gauss-Seidel sweep (same FE order, same iterates); per sweep it reads only the int32 code columns
-// (in FE-j-sorted order, built once with a radix argsort) and gathers rows of the other FEs' tables
-// (L1/L2-resident for low-cardinality FEs) -- no column traffic and no floating-point scatter.
+// (in FE-j-sorted order, built once with a radix argsort; the data rows themselves are never permuted) and
+// gathers rows of the other FEs' tables (L1/L2-resident) -- no column traffic, no floating-point scatter.
+// S0 is one by-key pass over the columns in their original order: shared-memory bins for low-cardinality
+// FEs, run-merged RED.ADD.F64 into the L2-resident table otherwise.
 // Because every FE's rows are visited in sorted order the group sums are segmented reductions:
 // thread-local run compression, a warp-shuffle segmented scan, and one RED.ADD.F64 per (warp, group)
 // for groups that straddle warps.  After convergence one streaming pass applies the tables to the
@@ -99,6 +101,34 @@ __global__ void __launch_bounds__(PJ_T) k_segsum(const int32_t* __restrict__ key
 }
 
 // alpha <- (S0 - acc) / nsum ; acc <- 0
+// Low-cardinality FE: per-CTA privatised fp64 bins in shared memory (G*NC*8 bytes), rows in their original
+// order with coalesced column loads; the CTA's bins are flushed with one RED.ADD.F64 per non-zero bin.
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_binsum_smem(const int32_t* __restrict__ key, ColPtrs cols,
+                                                     const double* __restrict__ w, int64_t n, int G,
+                                                     double* __restrict__ acc, int ld_acc, int acc_col0) {
+  extern __shared__ double bins[];
+  for (int i = threadIdx.x; i < G * NC; i += blockDim.x) bins[i] = 0.0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int g = __ldcs(key + i);
+    double we = 1.0;
+    if (WEIGHTED) we = __ldcs(w + i);
+    double* b = bins + (size_t)g * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double x = __ldcs(cols.col[c] + i);
+      atomicAdd(b + c, WEIGHTED ? x * we : x);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * NC; i += blockDim.x) {
+    double v = bins[i];
+    if (v != 0.0) atomicAdd(acc + (size_t)(i / NC) * ld_acc + acc_col0 + (i % NC), v);
+  }
+}
+
 // delta_max (nullable): max |alpha_new - alpha_old| = largest weighted group mean of the residual just removed
 __global__ void __launch_bounds__(256) k_finalize(double* __restrict__ alpha, double* __restrict__ acc,
                                                   const double* __restrict__ S0, const double* __restrict__ nsum,
@@ -238,6 +268,36 @@ static void launch_segsum(lfe_ctx* h, int nc, const int32_t* key, const ColPtrs&
   h->n_launches += 1;
 }
 
+constexpr int BINSUM_MAX_DOUBLES = 8192;  // 64 KB of shared-memory bins -> 3 CTAs per SM
+
+// group sums of columns in ORIGINAL row order: shared-memory bins for small G, run-merged RED otherwise
+template <bool WEIGHTED>
+static void launch_groupsum(lfe_ctx* h, int nc, const int32_t* key, int64_t G, const ColPtrs& cols, const double* w,
+                            int64_t n, double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
+  if (n <= 0) return;
+  if (G * nc <= BINSUM_MAX_DOUBLES) {
+    size_t smem = (size_t)G * nc * sizeof(double);
+    int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : 3);
+    int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), per_sm);
+#define BS_CASE(NC_)                                                                                              \
+  case NC_:                                                                                                       \
+    if (smem > 48 * 1024)                                                                                         \
+      CUDA_CHECK(cudaFuncSetAttribute(k_binsum_smem<NC_, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                \
+    k_binsum_smem<NC_, WEIGHTED><<<blocks, 256, smem, s>>>(key, cols, w, n, (int)G, acc, ld_acc, acc_col0);      \
+    break;
+    switch (nc) {
+      BS_CASE(1) BS_CASE(2) BS_CASE(3) BS_CASE(4) BS_CASE(5) BS_CASE(6) BS_CASE(7) BS_CASE(8)
+      default: LFE_THROW(LFE_ERR_ARG, "launch_groupsum: nc=%d", nc);
+    }
+#undef BS_CASE
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  } else {
+    launch_segsum<WEIGHTED>(h, nc, key, cols, nullptr, w, n, acc, ld_acc, acc_col0, s);
+  }
+}
+
 static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const ApplyTabs& T, int64_t n, int ldc, int col0,
                          cudaStream_t s) {
   int blocks = launch_blocks(h, ceil_div64(n, 256), 8);
@@ -282,7 +342,7 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
       FEState& S = st[j];
       S.G = n_groups[j];
       LFE_REQUIRE(S.G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
-      S.identity = prim_is_sorted(h, codes[j], n, s) != 0;
+      S.identity = (F == 1) || prim_is_sorted(h, codes[j], n, s) != 0;   // F == 1 never projects: no entry list
       if (S.identity) {
         S.key = codes[j];
         for (int k = 0; k < F; ++k) S.oth[k] = codes[k];
@@ -325,18 +385,18 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
         int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
         ColPtrs cp;
         for (int c = 0; c < nc; ++c) cp.col[c] = cols[c0 + c];
-        if (weighted) launch_segsum<true>(h, nc, S.key, cp, S.identity ? nullptr : S.perm.p, S.w, n, S.S0, C, c0, s);
-        else launch_segsum<false>(h, nc, S.key, cp, S.identity ? nullptr : S.perm.p, nullptr, n, S.S0, C, c0, s);
+        if (weighted) launch_groupsum<true>(h, nc, codes[j], S.G, cp, weights, n, S.S0, C, c0, s);
+        else launch_groupsum<false>(h, nc, codes[j], S.G, cp, nullptr, n, S.S0, C, c0, s);
       }
       if (weighted) {
         // n_j = sum of weights per group; unweighted y sums for the convergence check
         S.nsum.zero();
-        ColPtrs cw; cw.col[0] = S.w;
-        launch_segsum<false>(h, 1, S.key, cw, nullptr, nullptr, n, S.nsum, 1, 0, s);
+        ColPtrs cw; cw.col[0] = weights;
+        launch_groupsum<false>(h, 1, codes[j], S.G, cw, nullptr, n, S.nsum, 1, 0, s);
         S.S0u_buf.alloc(S.G, s);
         S.S0u_buf.zero();
         ColPtrs cy; cy.col[0] = cols[0];
-        launch_segsum<false>(h, 1, S.key, cy, S.identity ? nullptr : S.perm.p, nullptr, n, S.S0u_buf, 1, 0, s);
+        launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
         S.cnt = S.cnt_buf; S.S0u = S.S0u_buf; S.ld_s0u = 1;
       } else {
         S.cnt = S.nsum; S.S0u = S.S0; S.ld_s0u = C;

@@ -313,22 +313,27 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
     KERNEL_CHECK();
     h->n_launches += 1;
   }
+  std::vector<unsigned long long> hacc(1 + F);
+  CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
   if (fe_dims_out) {
+    const bool dropped = (int64_t)hacc[0] < n;
     for (int j = 0; j < F; ++j) {
-      CUDA_CHECK(cudaMemsetAsync(cnts[j].p, 0, (size_t)n_groups[j] * sizeof(uint32_t), s));
-      if (n > 0) {
+      if (n <= 0) break;
+      if (dropped) {  // a group survives iff it still has a kept row: one more pass over the codes
+        CUDA_CHECK(cudaMemsetAsync(cnts[j].p, 0, (size_t)n_groups[j] * sizeof(uint32_t), s));
         k_mark_kept_groups<<<blocks, 256, 0, s>>>(codes[j], keep, n, cnts[j]);
         KERNEL_CHECK();
-        int bg = launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8);
-        k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], acc.p + 1 + j);
-        KERNEL_CHECK();
-        h->n_launches += 2;
-      }
+        h->n_launches += 1;
+      }  // else: nothing dropped, the non-empty groups of the histogram are the answer
+      int bg = launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8);
+      k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], acc.p + 1 + j);
+      KERNEL_CHECK();
+      h->n_launches += 1;
     }
+    CUDA_CHECK(cudaMemcpyAsync(hacc.data() + 1, acc.p + 1, F * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
   }
-  std::vector<unsigned long long> hacc(1 + F);
-  CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, (1 + F) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
   *n_keep_out = (int64_t)hacc[0];
   if (fe_dims_out)
     for (int j = 0; j < F; ++j) fe_dims_out[j] = (int64_t)hacc[1 + j];

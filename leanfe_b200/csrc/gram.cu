@@ -21,7 +21,7 @@ struct GramCols {
 
 template <int P, bool INTERCEPT>
 __global__ void __launch_bounds__(GR_T) k_gram_tri(GramCols cols, const double* __restrict__ w,
-                                                   const double* __restrict__ r, int64_t n,
+                                                   const double* __restrict__ r, int64_t n, int64_t ld,
                                                    double* __restrict__ partials) {
   constexpr int T = P * (P + 1) / 2;
   constexpr int NCOL = INTERCEPT ? P - 1 : P;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(GR_T) k_gram_tri(GramCols cols, const double* 
     double z[P];
     if (INTERCEPT) z[0] = 1.0;
 #pragma unroll
-    for (int c = 0; c < NCOL; ++c) z[c + (INTERCEPT ? 1 : 0)] = __ldcs(cols.col[c] + i);
+    for (int c = 0; c < NCOL; ++c) z[c + (INTERCEPT ? 1 : 0)] = __ldcs(cols.col[c] + i * ld);
     double om = 1.0;
     if (w) om = __ldcs(w + i);
     if (r) {
@@ -73,7 +73,7 @@ constexpr int GG_PAIRS = 20;  // pairs per thread -> T <= 5120 (P <= 100)
 
 __global__ void __launch_bounds__(GR_T) k_gram_generic(const double* const* __restrict__ cols, int ncol,
                                                        int intercept, const double* __restrict__ w,
-                                                       const double* __restrict__ r, int64_t n,
+                                                       const double* __restrict__ r, int64_t n, int64_t stride,
                                                        double* __restrict__ partials) {
   extern __shared__ double tile[];  // [GG_ROWS][P+1] ; last column = omega
   const int P = ncol + intercept;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(GR_T) k_gram_generic(const double* const* __re
         } else if (intercept && c == 0) {
           v = 1.0;
         } else {
-          v = cols[c - intercept][i];
+          v = cols[c - intercept][i * stride];
         }
       }
       tile[rr * ld + c] = v;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_gram_final(const double* __restrict__ p
 
 // Z' diag(w * r^2) Z ; cols are host pointers to device columns
 void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* w, const double* r,
-               int add_intercept, double* gram_out, cudaStream_t s) {
+               int add_intercept, double* gram_out, cudaStream_t s, int64_t stride) {
   const int P = C + (add_intercept ? 1 : 0);
   LFE_REQUIRE(P >= 1 && C <= GR_MAXCOLS, "lfe_gram: %d columns unsupported (max %d)", C, GR_MAXCOLS);
   const int T = P * (P + 1) / 2;
@@ -167,8 +167,8 @@ void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const do
     for (int c = 0; c < C; ++c) gc.col[c] = cols[c];
 #define TRI_CASE(P_)                                                                                   \
   case P_:                                                                                             \
-    if (add_intercept) k_gram_tri<P_, true><<<blocks, GR_T, 0, s>>>(gc, w, r, n, partials);           \
-    else k_gram_tri<P_, false><<<blocks, GR_T, 0, s>>>(gc, w, r, n, partials);                        \
+    if (add_intercept) k_gram_tri<P_, true><<<blocks, GR_T, 0, s>>>(gc, w, r, n, stride, partials);           \
+    else k_gram_tri<P_, false><<<blocks, GR_T, 0, s>>>(gc, w, r, n, stride, partials);                        \
     break;
     switch (P) {
       TRI_CASE(1) TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8) TRI_CASE(9)
@@ -187,7 +187,7 @@ void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const do
     CUDA_CHECK(cudaMemcpyAsync(dcols.p, cols, C * sizeof(double*), cudaMemcpyHostToDevice, s));
     size_t smem = (size_t)GG_ROWS * (P + 1) * sizeof(double);
     CUDA_CHECK(cudaFuncSetAttribute(k_gram_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gram_generic<<<blocks, GR_T, smem, s>>>(dcols, C, add_intercept ? 1 : 0, w, r, n, partials);
+    k_gram_generic<<<blocks, GR_T, smem, s>>>(dcols, C, add_intercept ? 1 : 0, w, r, n, stride, partials);
     KERNEL_CHECK();
     k_gram_final<<<1, 256, 0, s>>>(partials, blocks, P, gram_out);
     KERNEL_CHECK();
@@ -199,7 +199,7 @@ void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const do
 void gram_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* weights, int add_intercept,
                double* gram_out, cudaStream_t s) {
   PhaseTimer t(h, s, 9);
-  gram_core(h, cols, C, n, weights, nullptr, add_intercept, gram_out, s);
+  gram_core(h, cols, C, n, weights, nullptr, add_intercept, gram_out, s, 1);
   if (h->world > 1) {
     int P = C + (add_intercept ? 1 : 0);
     comm_allreduce(h, gram_out, (int64_t)P * P, 0, s);

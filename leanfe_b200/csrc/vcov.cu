@@ -4,12 +4,12 @@
 // One streaming pass computes r = y - b0 - X beta, sum r^2, sum w r^2 and the shifted moments of y.
 // HC1 reuses the Gram kernels with omega = w r^2.  Cluster scores S_g = sum_{i in g} w x_i r_i are a
 // by-key reduction (segmented when the cluster is the row sort key, RED.ADD.F64 otherwise) into a
-// column-major G x k table whose Gram is the meat.  The k x k sandwich algebra runs in one CTA.
+// row-major G x k table (one or two 32-byte sectors per row) whose Gram is the meat.  The k x k sandwich algebra runs in one CTA.
 #include "common.cuh"
 #include "segreduce.cuh"
 
 void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* w, const double* r,
-               int add_intercept, double* gram_out, cudaStream_t s);
+               int add_intercept, double* gram_out, cudaStream_t s, int64_t stride = 1);
 int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
                            void* uniques, int64_t uniques_cap, cudaStream_t s);
 void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);
@@ -72,11 +72,11 @@ __global__ void k_stats_from_raw(const double* __restrict__ raw, double n_total,
   }
 }
 
-// S[c * G + key] += w * x_c * r      (any key order; runs of equal keys are merged first)
+// S[key * K + c] += w * x_c * r   (row-major G x K; any key order; runs of equal keys are merged first)
 template <int NC>
 __global__ void __launch_bounds__(PJ_T) k_scores(const int32_t* __restrict__ key, ColPtrs X,
                                                  const double* __restrict__ r, const double* __restrict__ w,
-                                                 int64_t n, double* __restrict__ S, int64_t G, int col0, bool vec_codes) {
+                                                 int64_t n, double* __restrict__ S, int K, int col0, bool vec_codes) {
   const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
     const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(PJ_T) k_scores(const int32_t* __restrict__ key
 #pragma unroll
       for (int c = 0; c < NC; ++c) v[e][c] = valid ? __ldcs(X.col[c] + base + e) * rr : 0.0;
     }
-    segmented_flush<NC>(k, v, S, 1, col0, G);
+    segmented_flush<NC>(k, v, S, K, col0, 1);
   }
 }
 
@@ -157,7 +157,7 @@ static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* 
     ColPtrs cp;
     for (int c = 0; c < nc; ++c) cp.col[c] = xcols[c0 + c];
 #define SC_CASE(NC_) \
-  case NC_: k_scores<NC_><<<blocks, PJ_T, 0, s>>>(cl, cp, resid, w, n, S, G, c0, vec); break;
+  case NC_: k_scores<NC_><<<blocks, PJ_T, 0, s>>>(cl, cp, resid, w, n, S, k, c0, vec); break;
     switch (nc) {
       SC_CASE(1) SC_CASE(2) SC_CASE(3) SC_CASE(4) SC_CASE(5) SC_CASE(6) SC_CASE(7) SC_CASE(8)
     }
@@ -167,8 +167,8 @@ static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* 
   }
   if (h->world > 1) comm_allreduce(h, S, G * k, 0, s);
   std::vector<const double*> sc(k);
-  for (int c = 0; c < k; ++c) sc[c] = S.p + (size_t)c * G;
-  gram_core(h, sc.data(), k, G, nullptr, nullptr, 0, meat_dev, s);
+  for (int c = 0; c < k; ++c) sc[c] = S.p + c;   // row-major table: column c has stride k
+  gram_core(h, sc.data(), k, G, nullptr, nullptr, 0, meat_dev, s, k);
 }
 
 static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, cudaStream_t s) {
