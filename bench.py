@@ -177,6 +177,8 @@ def main():
         host[k_] = t
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     kw = dict(formula=FORMULA, vcov="cluster", cluster_cols=["unit"], strategy="alt_proj")
+    if world > 1:
+        kw["local_fe"] = "unit"      # rows are sharded by unit: its tables, counts and cluster scores stay rank-local
 
     def barrier():
         if world > 1:

@@ -45,8 +45,14 @@ enum { LFE_I32 = 0, LFE_I64 = 1, LFE_U32 = 2, LFE_U64 = 3, LFE_F64 = 4, LFE_U8 =
 /* code order: 0 = rank among ascending sorted uniques (== np.unique(..., return_inverse=True)),
  *             1 = first-appearance rank (== pandas.factorize)                                    */
 enum { LFE_ORDER_SORTED = 0, LFE_ORDER_FIRST = 1 };
+/* OR-ed into `order`: with a communicator attached, every rank gets codes from ONE shared code space
+ * (keys need not be present on every rank); sorted-rank order only, key range < 2^28.             */
+#define LFE_ORDER_GLOBAL 0x100
 /* vcov kinds (python/leanfe/std_errors.py:83-176) */
 enum { LFE_VCOV_IID = 0, LFE_VCOV_HC1 = 1, LFE_VCOV_CLUSTER = 2 };
+/* OR-ed into vcov_kind (multi-GPU, one-way): the cluster's groups never span ranks (e.g. cluster == shard
+ * key), so only the k x k meat is all-reduced instead of the G x k score table                      */
+#define LFE_VCOV_CLUSTER_LOCAL 0x100
 
 #define LFE_MAX_FE 8
 #define LFE_MAX_CLUSTER_WAYS 4
@@ -88,9 +94,12 @@ int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_gr
 /* ---- singleton filter -------------------------------------------------------------------------
  * Replaces: `lf.filter(all_horizontal(len().over(fe) > 1))` polars_impl.py:478-482 (434-435).
  * keep_out[i] = 1 iff every FE's group of row i has more than one row; ONE pass on the input.
- * fe_dims_out[j] (nullable) = number of distinct codes of FE j among kept rows (:531-534).       */
+ * fe_dims_out[j] (nullable) = number of distinct codes of FE j among kept rows (:531-534).
+ * n_keep_out[0] = kept rows on this rank, n_keep_out[1] = kept rows over all ranks.  With a
+ * communicator attached, group sizes of every FE except `local_fe` (-1: none) are summed over the
+ * ranks before the test and fe_dims are global.                                                  */
 int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
-                       int64_t n, uint8_t* keep_out, int64_t* n_keep_out /*[host]*/,
+                       int64_t n, int local_fe, uint8_t* keep_out, int64_t* n_keep_out /*[host] 2*/,
                        int64_t* fe_dims_out /*[host] F*/, void* stream);
 
 /* stable compaction of C double columns and K int32 columns by keep[]; outputs have n_keep rows */

@@ -14,8 +14,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblfe.so")
 
 # dtype / enum mirrors of include/lfe.h
 LFE_I32, LFE_I64, LFE_U32, LFE_U64, LFE_F64, LFE_U8 = 0, 1, 2, 3, 4, 5
-ORDER_SORTED, ORDER_FIRST = 0, 1
+ORDER_SORTED, ORDER_FIRST, ORDER_GLOBAL = 0, 1, 0x100
 VCOV_IID, VCOV_HC1, VCOV_CLUSTER = 0, 1, 2
+VCOV_CLUSTER_LOCAL = 0x100
 N_TIMERS = 16
 TIMER_NAMES = ["factorize", "counts_singletons", "compact", "sort", "gather", "demean_setup", "demean_sweeps",
                "demean_check", "demean_apply", "gram", "solve", "resid_vcov", "compress", "collectives", "_14", "_15"]
@@ -60,7 +61,7 @@ def load_library() -> C.CDLL:
     lib.lfe_get_counters.argtypes = [vp, P(i64)]
     lib.lfe_factorize.argtypes = [vp, vp, i32, i64, i32, vp, P(i64), vp, i64, vp]
     lib.lfe_group_counts.argtypes = [vp, vp, i64, i64, vp, vp]
-    lib.lfe_singleton_mask.argtypes = [vp, P(vp), P(i64), i32, i64, vp, P(i64), P(i64), vp]
+    lib.lfe_singleton_mask.argtypes = [vp, P(vp), P(i64), i32, i64, i32, vp, P(i64), P(i64), vp]
     lib.lfe_compact.argtypes = [vp, vp, i64, P(vp), P(vp), i32, P(vp), P(vp), i32, vp]
     lib.lfe_sort_rows.argtypes = [vp, vp, i64, i64, vp, P(i32), vp]
     lib.lfe_gather.argtypes = [vp, vp, i64, P(vp), P(vp), i32, P(vp), P(vp), i32, vp]

@@ -53,8 +53,14 @@ def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strateg
 
 def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, formula=None, strategy="auto",
                 weights=None, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None, device=None,
-                profile=False) -> LeanFEResult:
-    """Counterpart of ``leanfe_polars`` (polars_impl.py:287-301) on the device."""
+                profile=False, local_fe=None) -> LeanFEResult:
+    """Counterpart of ``leanfe_polars`` (polars_impl.py:287-301) on the device.
+
+    Multi-GPU (one process per GPU, ``Engine.comm_init_from_torch()`` called): ``data`` holds THIS rank's
+    rows, partitioned so that the groups of fixed effect ``local_fe`` never span ranks (shard by the
+    highest-cardinality FE).  All other FE tables, the Gram matrix and the meat are all-reduced over NCCL
+    inside liblfe; every rank returns the same result.
+    """
     t_start = time.perf_counter()
     if formula is not None:
         y_col, x_cols, fe_cols, factor_vars, interactions, instruments = parse_formula(formula)
@@ -102,9 +108,20 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             numeric[name] = to_device_f64(eng, frame.column(name))
         return numeric[name]
 
+    dist = eng.world > 1
+    if dist:
+        if local_fe is None or local_fe not in fe_cols:
+            raise ValueError("multi-GPU fit: pass local_fe=<the FE column rows are sharded by>")
+        if strategy not in ("alt_proj", "demean"):
+            raise NotImplementedError("multi-GPU fits support strategy='alt_proj' / 'demean' (pass it explicitly)")
+        if sample_frac is not None:
+            raise NotImplementedError("sample_frac is not supported in multi-GPU fits")
+
     def key(name, labels=False):
         if name not in keys or (labels and keys[name].labels is None):
-            keys[name] = to_device_key(eng, frame.column(name), want_labels=labels)
+            # multi-GPU: every key column except the shard key needs ONE code space shared by all ranks
+            keys[name] = to_device_key(eng, frame.column(name), want_labels=labels,
+                                       global_codes=dist and name != local_fe)
         return keys[name]
 
     y = num(y_col)
@@ -183,8 +200,12 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
         res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
     else:
+        lf = fe_cols.index(local_fe) if dist else -1
+        cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
+        if dist and cluster_cols and len(cluster_cols) > 1:
+            raise NotImplementedError("multi-way clustering is single-GPU only")
         res = _fit_fwl(eng, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, demean_tol,
-                       max_iter, formula, est_ratio)
+                       max_iter, formula, est_ratio, lf, cl_local)
     if profile:
         torch.cuda.synchronize(eng.device)
         res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
@@ -194,7 +215,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
 # ------------------------------------------------------------------------------------------------
 def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
-             formula, est_ratio) -> LeanFEResult:
+             formula, est_ratio, local_fe=-1, cl_local=False) -> LeanFEResult:
     """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression."""
     k = len(X)
     F = len(fe_keys)
@@ -209,7 +230,8 @@ def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, 
         codes = [f.codes for f in fe_keys]
         Gs = [f.n_groups for f in fe_keys]
         # singleton filter: one pass, all FEs (polars_impl.py:478-482)
-        keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs)
+        keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe)
+        n_obs_global = eng.last_n_keep_global
         owned = False
         if n_keep < y.numel():
             f_in = cols + ([w] if w is not None else [])
@@ -224,13 +246,17 @@ def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, 
             cols = [c.clone() for c in cols]          # lfe_demean works in place; never touch caller data
         order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
         if strategy == "demean":
-            iterations, _, _ = eng.demean(cols, codes, Gs, order, w, tol, 1, 2)
+            iterations, _, _ = eng.demean(cols, codes, Gs, order, w, tol, 1, 2, local_fe)
             iterations, converged = 1, True
             absorbed = fe_dims[0] - 1
         else:
-            iterations, _, converged = eng.demean(cols, codes, Gs, order, w, tol, max_iter, 3)
+            iterations, _, converged = eng.demean(cols, codes, Gs, order, w, tol, max_iter, 3, local_fe)
             absorbed = sum(fe_dims) - F
-    n_obs = cols[0].numel()
+        n_obs = n_obs_global
+    else:
+        n_obs = cols[0].numel()
+    if vkind == capi.VCOV_CLUSTER and cl_local:
+        vkind |= capi.VCOV_CLUSTER_LOCAL
     # regression on [1 | X~] (polars_impl.py:166-226)
     gram = eng.gram(cols[1:] + [cols[0]], w, add_intercept=True)       # order: 1, x.., y
     p = k + 1
@@ -242,7 +268,7 @@ def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, 
     host = torch.cat([beta_full, out["se"], out["stats"]]).cpu().numpy()
     beta, se, (rss, tss) = host[1:p], host[p:p + k], host[p + k:p + k + 2]
     n_clusters = None
-    if vkind == capi.VCOV_CLUSTER:
+    if (vkind & 0xFF) == capi.VCOV_CLUSTER:
         n_clusters = out["n_clusters"][0] if len(cl_keys) == 1 else tuple(out["n_clusters"])
     r2 = float(1 - rss / tss) if tss > 0 else None
     return LeanFEResult(coefs=dict(zip(x_cols, beta.tolist())), std_errors=dict(zip(x_cols, se.tolist())), n_obs=n_obs,

@@ -7,7 +7,7 @@
 int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
                            void* uniques, int64_t uniques_cap, cudaStream_t s);
 void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                         uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s);
+                         int local_fe, uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s);
 void compact_impl(lfe_ctx* h, const uint8_t* keep, int64_t n, const double* const* f64_in, double* const* f64_out,
                   int C, const int32_t* const* i32_in, int32_t* const* i32_out, int K, cudaStream_t s);
 void sort_rows_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t n_groups, int32_t* perm_out,
@@ -135,6 +135,11 @@ void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStre
   if (h->world <= 1 || count <= 0) return;
   NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, NCCL_FLOAT64, op_max ? NCCL_MAX : NCCL_SUM, h->nccl_comm, s));
 }
+// kind: 0 = uint32, 1 = uint64 ; op: 0 sum, 2 max, 3 min (NCCL numbering)
+void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s) {
+  if (h->world <= 1 || count <= 0) return;
+  NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, kind == 0 ? 3 : 5, op, h->nccl_comm, s));
+}
 
 // ---- exported functions -------------------------------------------------------------------------------
 extern "C" {
@@ -207,7 +212,8 @@ int lfe_factorize(lfe_handle h, const void* keys, int key_dtype, int64_t n, int 
   LFE_API_BEGIN
   LFE_REQUIRE(h && n_groups_out, "lfe_factorize: NULL argument");
   LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_factorize: n out of range");
-  LFE_REQUIRE(order == LFE_ORDER_SORTED || order == LFE_ORDER_FIRST, "lfe_factorize: bad order %d", order);
+  LFE_REQUIRE((order & ~LFE_ORDER_GLOBAL) == LFE_ORDER_SORTED || (order & ~LFE_ORDER_GLOBAL) == LFE_ORDER_FIRST,
+              "lfe_factorize: bad order %d", order);
   CUDA_CHECK(cudaSetDevice(h->device));
   int64_t G = factorize_dispatch(h, keys, key_dtype, n, order, codes_out, uniques_out, uniques_cap, S(stream));
   *n_groups_out = G;
@@ -227,11 +233,11 @@ int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_gr
 }
 
 int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                       uint8_t* keep_out, int64_t* n_keep_out, int64_t* fe_dims_out, void* stream) {
+                       int local_fe, uint8_t* keep_out, int64_t* n_keep_out, int64_t* fe_dims_out, void* stream) {
   LFE_API_BEGIN
   LFE_REQUIRE(h && codes && n_groups && keep_out && n_keep_out, "lfe_singleton_mask: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
-  singleton_mask_impl(h, codes, n_groups, F, n, keep_out, n_keep_out, fe_dims_out, S(stream));
+  singleton_mask_impl(h, codes, n_groups, F, n, local_fe, keep_out, n_keep_out, fe_dims_out, S(stream));
   LFE_API_END
 }
 

@@ -338,20 +338,52 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
   // ---- setup: per-FE sorted entry lists, counts, S0 --------------------------------------------
   {
     PhaseTimer t(h, s, 5);
+    // Entry lists.  The highest-cardinality FE ("big") is sorted first; every other FE is then sorted
+    // STABLY from the big-sorted sequence, so inside each of its groups the big FE's codes ascend and the
+    // gathers into the big FE's table walk memory monotonically.
+    int big = 0;
+    for (int j = 1; j < F; ++j)
+      if (n_groups[j] > n_groups[big]) big = j;
     for (int j = 0; j < F; ++j) {
-      FEState& S = st[j];
-      S.G = n_groups[j];
-      LFE_REQUIRE(S.G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
-      S.identity = (F == 1) || prim_is_sorted(h, codes[j], n, s) != 0;   // F == 1 never projects: no entry list
-      if (S.identity) {
-        S.key = codes[j];
-        for (int k = 0; k < F; ++k) S.oth[k] = codes[k];
-        S.w = weights;
-      } else {
+      st[j].G = n_groups[j];
+      LFE_REQUIRE(st[j].G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
+      st[j].identity = (F == 1) || prim_is_sorted(h, codes[j], n, s) != 0;   // F == 1 never projects
+    }
+    if (F == 2 && !weighted && !st[0].identity && !st[1].identity) {
+      // two FEs: sort (key, other code) pairs directly -- no row permutation, no gathers
+      const int sm = 1 - big;
+      FEState &B = st[big], &M = st[sm];
+      B.key_buf.alloc(n, s); B.oth_buf[sm].alloc(n, s);
+      prim_sort_pairs_u32(h, (const uint32_t*)codes[big], (const uint32_t*)codes[sm], n, bits_for((uint64_t)(B.G - 1)),
+                          (uint32_t*)B.key_buf.p, (uint32_t*)B.oth_buf[sm].p, s);
+      B.key = B.key_buf; B.oth[sm] = B.oth_buf[sm];
+      M.key_buf.alloc(n, s); M.oth_buf[big].alloc(n, s);
+      prim_sort_pairs_u32(h, (const uint32_t*)B.oth_buf[sm].p, (const uint32_t*)B.key_buf.p, n,
+                          bits_for((uint64_t)(M.G - 1)), (uint32_t*)M.key_buf.p, (uint32_t*)M.oth_buf[big].p, s);
+      M.key = M.key_buf; M.oth[big] = M.oth_buf[big];
+    } else {
+      const uint32_t* base_perm = nullptr;   // big-sorted order (nullptr = identity)
+      for (int step = 0; step < F; ++step) {
+        const int j = step == 0 ? big : (step <= big ? step - 1 : step);
+        FEState& S = st[j];
+        if (S.identity) {
+          S.key = codes[j];
+          for (int k = 0; k < F; ++k) S.oth[k] = codes[k];
+          S.w = weights;
+          continue;
+        }
         S.perm.alloc(n, s);
         S.key_buf.alloc(n, s);
-        prim_argsort_u32(h, (const uint32_t*)codes[j], n, bits_for((uint64_t)(S.G - 1)), S.perm,
-                         (uint32_t*)S.key_buf.p, s);
+        const int kb = bits_for((uint64_t)(S.G - 1));
+        if (j == big || base_perm == nullptr) {
+          prim_argsort_u32(h, (const uint32_t*)codes[j], n, kb, S.perm, (uint32_t*)S.key_buf.p, s);
+          if (j == big) base_perm = S.perm;
+        } else {
+          DevBuf<int32_t> kin(n, s);
+          prim_gather_i32(codes[j], base_perm, n, kin, s);
+          prim_sort_pairs_u32(h, (const uint32_t*)kin.p, base_perm, n, kb, (uint32_t*)S.key_buf.p, S.perm, s);
+          h->n_launches += 1;
+        }
         S.key = S.key_buf;
         for (int k = 0; k < F; ++k) {
           if (k == j) continue;
@@ -367,6 +399,9 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
           h->n_launches += 1;
         }
       }
+    }
+    for (int j = 0; j < F; ++j) {
+      FEState& S = st[j];
       size_t tab = (size_t)S.G * C;
       S.alpha.alloc(tab, s); S.S0.alloc(tab, s); S.acc.alloc(tab, s); S.nsum.alloc(S.G, s);
       S.alpha.zero(); S.S0.zero(); S.acc.zero();

@@ -7,6 +7,8 @@
 // passes; otherwise a stable LSD radix argsort of (key - min) does.
 #include "common.cuh"
 
+void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);  // api.cu
+
 // ---------------------------------------------------------------------------------------------
 // order-preserving uint64 image of a key
 // ---------------------------------------------------------------------------------------------
@@ -162,13 +164,21 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
   typedef typename KeyIO<DT>::T T;
   const T* keys = (const T*)keys_v;
   T* uniques = (T*)uniques_v;
-  if (n == 0) return 0;
+  const bool global = (order & LFE_ORDER_GLOBAL) != 0 && h->world > 1;
+  order &= ~LFE_ORDER_GLOBAL;
+  if (n == 0 && !global) return 0;
   int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
   DevBuf<unsigned long long> mm(2, s);
   unsigned long long init[2] = {~0ull, 0ull};
   CUDA_CHECK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-  k_minmax<DT><<<blocks, 256, 0, s>>>(keys, n, mm);
-  KERNEL_CHECK();
+  if (n > 0) {
+    k_minmax<DT><<<blocks, 256, 0, s>>>(keys, n, mm);
+    KERNEL_CHECK();
+  }
+  if (global) {  // one code space for all ranks: global key range, merged presence table
+    comm_allreduce_int(h, mm.p, 1, 1, 3, s);
+    comm_allreduce_int(h, mm.p + 1, 1, 1, 2, s);
+  }
   unsigned long long hmm[2];
   CUDA_CHECK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -179,15 +189,25 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
   unsigned long long direct_limit = (unsigned long long)(16 * n > (1 << 20) ? 16 * n : (1 << 20));
   if (direct_limit > (1ull << 28)) direct_limit = 1ull << 28;
   DevBuf<uint32_t> total(1, s);
+  if (global) {
+    LFE_REQUIRE(order == LFE_ORDER_SORTED, "lfe_factorize: LFE_ORDER_GLOBAL supports sorted-rank codes only");
+    LFE_REQUIRE(span < (1ull << 28), "lfe_factorize: LFE_ORDER_GLOBAL needs a key range < 2^28 (got %llu)", span);
+    direct_limit = 1ull << 28;
+  }
   if (span < direct_limit) {
     int64_t range = (int64_t)span + 1;
     DevBuf<uint32_t> flags(range, s), rank(range, s);
     flags.zero();
-    k_mark<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, flags);
-    KERNEL_CHECK();
+    if (n > 0) {
+      k_mark<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, flags);
+      KERNEL_CHECK();
+    }
+    if (global) comm_allreduce_int(h, flags.p, range, 0, 2, s);
     prim_exclusive_scan_u32(h, flags, rank, range, total, s);
-    k_lookup<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, rank, codes);
-    KERNEL_CHECK();
+    if (n > 0) {
+      k_lookup<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, rank, codes);
+      KERNEL_CHECK();
+    }
     uint32_t ht = 0;
     CUDA_CHECK(cudaMemcpyAsync(&ht, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -293,19 +313,23 @@ __global__ void __launch_bounds__(256) k_count_nonzero(const uint32_t* __restric
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
 }
 
+// Multi-GPU: group sizes of every FE except `local_fe` are summed over the ranks before the test; n_keep_out[0]
+// is the local, n_keep_out[1] the global number of kept rows; fe_dims are global.
 void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                         uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s) {
+                         int local_fe, uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s) {
   PhaseTimer t(h, s, 1);
   LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_singleton_mask: F=%d out of range", F);
+  const bool dist = h->world > 1;
   std::vector<DevBuf<uint32_t>> cnts(F);
   CodePtrs P;
   for (int j = 0; j < F; ++j) {
     cnts[j].alloc((size_t)n_groups[j], s);
     prim_histogram(h, codes[j], n, n_groups[j], cnts[j], s);
+    if (dist && j != local_fe) comm_allreduce_int(h, cnts[j].p, n_groups[j], 0, 0, s);
     P.code[j] = codes[j];
     P.cnt[j] = cnts[j];
   }
-  DevBuf<unsigned long long> acc(1 + F, s);
+  DevBuf<unsigned long long> acc(2 + F, s);
   acc.zero();
   int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
   if (n > 0) {
@@ -313,30 +337,47 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
     KERNEL_CHECK();
     h->n_launches += 1;
   }
-  std::vector<unsigned long long> hacc(1 + F);
-  CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(acc.p + 1, acc.p, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+  if (dist) comm_allreduce_int(h, acc.p + 1, 1, 1, 0, s);
+  std::vector<unsigned long long> hacc(2 + F);
+  CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   if (fe_dims_out) {
-    const bool dropped = (int64_t)hacc[0] < n;
+    // `dropped` must be the same decision on every rank (collectives below)
+    int64_t n_tot = n;
+    if (dist) {
+      DevBuf<unsigned long long> nt(1, s);
+      unsigned long long hn = (unsigned long long)n;
+      CUDA_CHECK(cudaMemcpyAsync(nt.p, &hn, sizeof(hn), cudaMemcpyHostToDevice, s));
+      comm_allreduce_int(h, nt.p, 1, 1, 0, s);
+      CUDA_CHECK(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      n_tot = (int64_t)hn;
+    }
+    const bool dropped = (int64_t)hacc[1] < n_tot;
     for (int j = 0; j < F; ++j) {
-      if (n <= 0) break;
       if (dropped) {  // a group survives iff it still has a kept row: one more pass over the codes
         CUDA_CHECK(cudaMemsetAsync(cnts[j].p, 0, (size_t)n_groups[j] * sizeof(uint32_t), s));
-        k_mark_kept_groups<<<blocks, 256, 0, s>>>(codes[j], keep, n, cnts[j]);
-        KERNEL_CHECK();
-        h->n_launches += 1;
-      }  // else: nothing dropped, the non-empty groups of the histogram are the answer
+        if (n > 0) {
+          k_mark_kept_groups<<<blocks, 256, 0, s>>>(codes[j], keep, n, cnts[j]);
+          KERNEL_CHECK();
+          h->n_launches += 1;
+        }
+        if (dist && j != local_fe) comm_allreduce_int(h, cnts[j].p, n_groups[j], 0, 2, s);
+      }  // else: nothing dropped, the non-empty groups of the (global) histogram are the answer
       int bg = launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8);
-      k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], acc.p + 1 + j);
+      k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], acc.p + 2 + j);
       KERNEL_CHECK();
       h->n_launches += 1;
+      if (dist && j == local_fe) comm_allreduce_int(h, acc.p + 2 + j, 1, 1, 0, s);
     }
-    CUDA_CHECK(cudaMemcpyAsync(hacc.data() + 1, acc.p + 1, F * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(hacc.data() + 2, acc.p + 2, F * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   }
-  *n_keep_out = (int64_t)hacc[0];
+  n_keep_out[0] = (int64_t)hacc[0];
+  n_keep_out[1] = (int64_t)hacc[1];
   if (fe_dims_out)
-    for (int j = 0; j < F; ++j) fe_dims_out[j] = (int64_t)hacc[1 + j];
+    for (int j = 0; j < F; ++j) fe_dims_out[j] = (int64_t)hacc[2 + j];
 }
 
 // ---------------------------------------------------------------------------------------------

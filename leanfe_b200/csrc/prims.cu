@@ -119,95 +119,6 @@ void prim_exclusive_scan_u32(lfe_ctx* h, const uint32_t* in, uint32_t* out, int6
   h->n_launches += 2;
 }
 
-// ---------------------------------------------------------------------------------------------
-// stable LSD radix argsort, 8 bits per pass
-// ---------------------------------------------------------------------------------------------
-constexpr int RS_T = 256;
-constexpr int RS_NW = RS_T / 32;
-constexpr int RS_I = 16;
-constexpr int RS_TILE = RS_T * RS_I;
-constexpr int RS_BINS = 256;
-
-template <typename KeyT>
-__global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift,
-                                                     uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t cnt[RS_BINS];
-  cnt[threadIdx.x] = 0;
-  __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * RS_TILE;
-  int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = 0; i < RS_I; ++i) {
-    int64_t idx = base + (int64_t)i * RS_T + threadIdx.x;
-    bool valid = idx < n;
-    uint32_t d = valid ? (uint32_t)((keys[idx] >> shift) & 0xFF) : (256u + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&cnt[d], __popc(peers));
-  }
-  __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(RS_T) k_radix_scatter(const KeyT* __restrict__ keys_in,
-                                                        const uint32_t* __restrict__ vals_in,
-                                                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                        int64_t n, int shift, const uint32_t* __restrict__ offsets,
-                                                        int nblocks) {
-  __shared__ uint32_t wcnt[RS_NW][RS_BINS];
-  __shared__ uint32_t dbase[RS_BINS];
-  for (int i = threadIdx.x; i < RS_NW * RS_BINS; i += RS_T) (&wcnt[0][0])[i] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lt = (1u << lane) - 1u;
-  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_I);
-  KeyT k[RS_I];
-  uint32_t v[RS_I];
-  uint32_t rk[RS_I];
-#pragma unroll
-  for (int r = 0; r < RS_I; ++r) {
-    int64_t idx = wbase + r * 32 + lane;
-    bool valid = idx < n;
-    k[r] = valid ? keys_in[idx] : (KeyT)0;
-    v[r] = valid ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
-  }
-#pragma unroll
-  for (int r = 0; r < RS_I; ++r) {
-    int64_t idx = wbase + r * 32 + lane;
-    bool valid = idx < n;
-    uint32_t d = valid ? (uint32_t)((k[r] >> shift) & 0xFF) : (256u + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t base = valid ? wcnt[warp][d] : 0u;
-    __syncwarp();
-    rk[r] = base + __popc(peers & lt);
-    if (valid && lane == (__ffs(peers) - 1)) wcnt[warp][d] = base + __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  {
-    int t = threadIdx.x;  // RS_T == RS_BINS
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < RS_NW; ++w) {
-      uint32_t c = wcnt[w][t];
-      wcnt[w][t] = run;
-      run += c;
-    }
-    dbase[t] = offsets[(size_t)t * nblocks + blockIdx.x];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RS_I; ++r) {
-    int64_t idx = wbase + r * 32 + lane;
-    if (idx < n) {
-      uint32_t d = (uint32_t)((k[r] >> shift) & 0xFF);
-      uint32_t pos = dbase[d] + wcnt[warp][d] + rk[r];
-      if (keys_out) keys_out[pos] = k[r];
-      vals_out[pos] = v[r];
-    }
-  }
-}
-
 __global__ void k_iota(uint32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = (uint32_t)i;
@@ -218,49 +129,6 @@ void prim_iota_u32(uint32_t* p, int64_t n, cudaStream_t s) {
   int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
   k_iota<<<blocks, 256, 0, s>>>(p, n);
   KERNEL_CHECK();
-}
-
-template <typename KeyT>
-static void argsort_impl(lfe_ctx* h, const KeyT* keys, int64_t n, int key_bits, uint32_t* perm_out,
-                         KeyT* keys_sorted_out, cudaStream_t s) {
-  if (n <= 0) return;
-  int npass = (key_bits + 7) / 8;
-  if (npass == 0) {
-    prim_iota_u32(perm_out, n, s);
-    if (keys_sorted_out) CUDA_CHECK(cudaMemcpyAsync(keys_sorted_out, keys, n * sizeof(KeyT), cudaMemcpyDeviceToDevice, s));
-    h->n_launches += 1;
-    return;
-  }
-  int nblocks = (int)ceil_div64(n, RS_TILE);
-  DevBuf<uint32_t> hist((size_t)RS_BINS * nblocks, s);
-  DevBuf<KeyT> ka(npass > 1 ? n : 0, s), kb(npass > 2 ? n : 0, s);
-  DevBuf<uint32_t> va(npass > 1 ? n : 0, s);
-  const KeyT* kin = keys;
-  const uint32_t* vin = nullptr;
-  for (int p = 0; p < npass; ++p) {
-    bool last = (p == npass - 1);
-    // value ping-pong so that the last pass lands in perm_out
-    uint32_t* vout = (((npass - 1 - p) & 1) == 0) ? perm_out : va.p;
-    KeyT* kout = last ? keys_sorted_out : ((p & 1) == 0 ? ka.p : kb.p);
-    int shift = p * 8;
-    k_radix_hist<KeyT><<<nblocks, RS_T, 0, s>>>(kin, n, shift, hist, nblocks);
-    KERNEL_CHECK();
-    prim_exclusive_scan_u32(h, hist, hist, (int64_t)RS_BINS * nblocks, nullptr, s);
-    k_radix_scatter<KeyT><<<nblocks, RS_T, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
-    KERNEL_CHECK();
-    h->n_launches += 2;
-    kin = kout;
-    vin = vout;
-  }
-}
-
-void prim_argsort_u32(lfe_ctx* h, const uint32_t* keys, int64_t n, int key_bits, uint32_t* perm_out,
-                      uint32_t* keys_sorted_out, cudaStream_t s) {
-  argsort_impl<uint32_t>(h, keys, n, key_bits, perm_out, keys_sorted_out, s);
-}
-void prim_argsort_u64(lfe_ctx* h, const uint64_t* keys, int64_t n, int key_bits, uint32_t* perm_out,
-                      uint64_t* keys_sorted_out, cudaStream_t s) {
-  argsort_impl<uint64_t>(h, keys, n, key_bits, perm_out, keys_sorted_out, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -146,7 +146,7 @@ __global__ void k_scale_se(const double* __restrict__ V, int k, double scale, co
 }
 
 static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* const* xcols, int k, const double* resid,
-                        const double* w, int64_t n, double* meat_dev, cudaStream_t s) {
+                        const double* w, int64_t n, double* meat_dev, cudaStream_t s, bool cl_local = false) {
   DevBuf<double> S((size_t)G * k, s);
   S.zero();
   int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
@@ -165,13 +165,17 @@ static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* 
     KERNEL_CHECK();
     h->n_launches += 1;
   }
-  if (h->world > 1) comm_allreduce(h, S, G * k, 0, s);
+  // multi-GPU: clusters shared by ranks -> sum the score table; rank-local clusters -> sum the k x k meats
+  if (h->world > 1 && !cl_local) comm_allreduce(h, S, G * k, 0, s);
   std::vector<const double*> sc(k);
   for (int c = 0; c < k; ++c) sc[c] = S.p + c;   // row-major table: column c has stride k
   gram_core(h, sc.data(), k, G, nullptr, nullptr, 0, meat_dev, s, k);
+  if (h->world > 1 && cl_local) comm_allreduce(h, meat_dev, (int64_t)k * k, 0, s);
 }
 
-static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, cudaStream_t s) {
+void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);
+static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, cudaStream_t s,
+                             bool cl_local = false) {
   DevBuf<uint32_t> present(G, s);
   present.zero();
   DevBuf<unsigned long long> tot(1, s);
@@ -181,15 +185,10 @@ static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_
     k_count_present<<<blocks, 256, 0, s>>>(codes, n, present);
     KERNEL_CHECK();
   }
-  if (h->world > 1) {
-    // presence flags are combined across ranks through a double buffer (counts stay exact: 0/1 sums < 2^53)
-    DevBuf<double> pd(G, s);
-    prim_u32_to_f64(h, present, G, pd, s);
-    comm_allreduce(h, pd, G, 1, s);
-    prim_f64_to_u32(h, pd, G, present, s);
-  }
+  if (h->world > 1 && !cl_local) comm_allreduce_int(h, present.p, G, 0, 2, s);   // shared code space: OR the flags
   k_sum_u32<<<launch_blocks(h, ceil_div64(G, 1024), 8), 256, 0, s>>>(present, G, tot);
   KERNEL_CHECK();
+  if (h->world > 1 && cl_local) comm_allreduce_int(h, tot.p, 1, 1, 0, s);          // disjoint clusters: add the counts
   h->n_launches += 2;
   unsigned long long ht = 0;
   CUDA_CHECK(cudaMemcpyAsync(&ht, tot.p, sizeof(ht), cudaMemcpyDeviceToHost, s));
@@ -203,13 +202,14 @@ static int64_t count_present(lfe_ctx* h, const int32_t* codes, int64_t n, int64_
 static void cluster_sandwich(lfe_ctx* h, const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W,
                              const double* const* xc, int k, const double* r, const double* w, int64_t n,
                              const double* Binv, int ssc, int64_t n_obs, int64_t df_resid, double* V, double* tmp,
-                             double* meat, double* se_out, double* vcov_out, int64_t* n_clusters_out, cudaStream_t s) {
+                             double* meat, double* se_out, double* vcov_out, int64_t* n_clusters_out, cudaStream_t s,
+                             bool cl_local = false) {
   if (W == 1) {
     // std_errors.py:289-347 / compress.py:922-953
-    int64_t G = count_present(h, cl_codes[0], n, n_cl_groups[0], s);
+    int64_t G = count_present(h, cl_codes[0], n, n_cl_groups[0], s, cl_local);
     if (n_clusters_out) n_clusters_out[0] = G;
     LFE_REQUIRE(G > 1, "clustered vcov: a single cluster (division by zero in G/(G-1))");
-    scores_meat(h, cl_codes[0], n_cl_groups[0], xc, k, r, w, n, meat, s);
+    scores_meat(h, cl_codes[0], n_cl_groups[0], xc, k, r, w, n, meat, s, cl_local);
     k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
     KERNEL_CHECK();
     double adj = (double)G / (double)(G - 1);
@@ -273,9 +273,11 @@ void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, co
                      const double* weights, int ssc, int64_t n_obs, int64_t df_resid, double* se_out, double* vcov_out,
                      double* stats_out, double* resid_out, int64_t* n_clusters_out, cudaStream_t s) {
   PhaseTimer t(h, s, 11);
+  const bool cl_local = (vcov_kind & LFE_VCOV_CLUSTER_LOCAL) != 0;
+  vcov_kind &= ~LFE_VCOV_CLUSTER_LOCAL;
   LFE_REQUIRE(k >= 0 && k <= RV_MAXK, "lfe_resid_vcov: k=%d out of range", k);
   LFE_REQUIRE(vcov_kind >= 0 && vcov_kind <= 2, "lfe_resid_vcov: unknown vcov kind %d", vcov_kind);
-  LFE_REQUIRE(n >= 1, "lfe_resid_vcov: no rows");
+  LFE_REQUIRE(n >= 1 || h->world > 1, "lfe_resid_vcov: no rows");
   if (vcov_kind == LFE_VCOV_CLUSTER) LFE_REQUIRE(W >= 1 && W <= LFE_MAX_CLUSTER_WAYS, "lfe_resid_vcov: cluster_cols required (1..%d ways)", LFE_MAX_CLUSTER_WAYS);
   DevBuf<double> resid_buf;
   double* resid = resid_out;
@@ -323,7 +325,7 @@ void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, co
     return;
   }
   cluster_sandwich(h, cl_codes, n_cl_groups, W, xc.data(), k, resid, weights, n, Binv, ssc, n_obs, df_resid, V, tmp,
-                   meat, se_out, vcov_out, n_clusters_out, s);
+                   meat, se_out, vcov_out, n_clusters_out, s, cl_local);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -117,17 +117,18 @@ class Engine:
         capi.check(self.lib.lfe_group_counts(self.h, self._p(codes), codes.numel(), n_groups, self._p(out), self.stream))
         return out
 
-    def singleton_mask(self, codes: list[torch.Tensor], n_groups: list[int]):
-        """-> (keep uint8, n_keep, fe_dims)"""
+    def singleton_mask(self, codes: list[torch.Tensor], n_groups: list[int], local_fe: int = -1):
+        """-> (keep uint8, n_keep on this rank, fe_dims).  ``self.last_n_keep_global`` = kept rows over all ranks."""
         self._check_dev(*codes)
         n = codes[0].numel()
         keep = self.empty(n, torch.uint8)
-        n_keep = C.c_int64(0)
+        n_keep = (C.c_int64 * 2)()
         dims = (C.c_int64 * len(codes))()
         capi.check(self.lib.lfe_singleton_mask(self.h, capi.ptr_array([c.data_ptr() for c in codes]),
-                                               capi.i64_array(n_groups), len(codes), n, self._p(keep),
-                                               C.byref(n_keep), dims, self.stream))
-        return keep, int(n_keep.value), tuple(int(d) for d in dims)
+                                               capi.i64_array(n_groups), len(codes), n, int(local_fe), self._p(keep),
+                                               n_keep, dims, self.stream))
+        self.last_n_keep_global = int(n_keep[1])
+        return keep, int(n_keep[0]), tuple(int(d) for d in dims)
 
     def compact(self, keep: torch.Tensor, n_keep: int, f64: list[torch.Tensor], i32: list[torch.Tensor]):
         self._check_dev(keep, *f64, *i32)

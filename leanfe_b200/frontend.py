@@ -97,9 +97,14 @@ def to_device_f64(eng: Engine, col) -> torch.Tensor:
     return t.contiguous()
 
 
-def to_device_key(eng: Engine, col, want_labels: bool = False) -> KeyColumn:
-    """Factorise a key column to sorted-rank codes (== np.unique(..., return_inverse=True))."""
+def to_device_key(eng: Engine, col, want_labels: bool = False, global_codes: bool = False) -> KeyColumn:
+    """Factorise a key column to sorted-rank codes (== np.unique(..., return_inverse=True)).
+
+    ``global_codes`` (multi-GPU): codes come from one code space shared by all ranks (LFE_ORDER_GLOBAL).
+    """
     if _is_stringlike(col):
+        if global_codes:
+            raise NotImplementedError("multi-GPU fits need numeric ids for the non-shard key columns")
         # strings stay on the host: dictionary-encode there, ship int32 codes (SURVEY 7 'hard parts')
         uniq, inv = np.unique(col, return_inverse=True)
         codes = torch.from_numpy(inv.reshape(-1).astype(np.int32)).to(eng.device, non_blocking=True)
@@ -123,7 +128,8 @@ def to_device_key(eng: Engine, col, want_labels: bool = False) -> KeyColumn:
         t = t.to(torch.float64)
     elif t.dtype == torch.bool:
         t = t.to(torch.uint8)
-    codes, G, uniq = eng.factorize(t, capi.ORDER_SORTED, want_uniques=want_labels, uniques_cap=1 << 16)
+    order = capi.ORDER_SORTED | (capi.ORDER_GLOBAL if global_codes else 0)
+    codes, G, uniq = eng.factorize(t, order, want_uniques=want_labels, uniques_cap=1 << 16)
     labels = uniq.cpu().tolist() if want_labels else None
     return KeyColumn(codes, G, labels)
 

@@ -1,0 +1,73 @@
+"""Multi-GPU parity check, run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py
+
+Every rank holds the rows of a disjoint block of units (the shard key); the fit must equal the oracle's
+single-process fit of the whole panel (beta 1e-8, SE 1e-6, equal iteration count) and be identical on
+all ranks.  Exit code 0 on success.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from leanfe_b200 import leanfe
+    from leanfe_b200.engine import get_engine
+    from leanfe_b200.sharding import shard_rows_by_key
+    from oracle import ref_numpy as O
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = get_engine(local)
+    eng.comm_init_from_torch()
+
+    rng = np.random.default_rng(123)                      # same panel on every rank
+    N, G1, G2 = 600_000, 12_000, 60
+    unit = rng.integers(0, G1, N) * 3 + 7                 # non-dense ids
+    time_ = rng.integers(0, G2, N)
+    time_[unit < 40] = 1                                   # some periods exist on one shard only
+    a, g = rng.normal(size=G1 * 3 + 8), rng.normal(size=G2)
+    x1, x2 = rng.normal(size=N) + 0.5 * a[unit], rng.normal(size=N) - 0.3 * a[unit]
+    y = 1.5 * x1 - 0.7 * x2 + a[unit] + g[time_] + rng.normal(size=N) * (1 + 0.3 * (unit % 5))
+    unit[:50] = np.arange(900_000, 900_050)               # singletons -> dropped
+    full = dict(y=y, x1=x1, x2=x2, unit=unit, time=time_)
+    mine = shard_rows_by_key(unit, world)[rank]
+    shard = {k: v[mine] for k, v in full.items()}
+
+    failures = []
+    for vc, cl in (("iid", None), ("hc1", None), ("cluster", ["unit"]), ("cluster", ["time"])):
+        kw = dict(formula="y ~ x1 + x2 | unit + time", vcov=vc, cluster_cols=cl, strategy="alt_proj")
+        res = leanfe(shard, local_fe="unit", **kw)
+        ref = O.leanfe_oracle(full, **kw)
+        b, eb = np.array(list(res.coefs.values())), np.array(list(ref["coefs"].values()))
+        s, es = np.array(list(res.std_errors.values())), np.array(list(ref["std_errors"].values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.iterations == ref["iterations"] and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and tuple(res.fe_dims) == tuple(ref["fe_dims"]) and res.n_clusters == ref["n_clusters"])
+        # identical on all ranks
+        t = torch.tensor(list(b) + list(s), dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and bool(torch.equal(lo, hi))
+        if not ok:
+            failures.append((vc, cl, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs, ref["n_obs"],
+                             res.fe_dims, ref["fe_dims"], res.n_clusters, ref["n_clusters"]))
+    if rank == 0:
+        print("multigpu_check:", "OK" if not failures else f"FAILED {failures}", f"(world={world})")
+    dist.destroy_process_group()
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
