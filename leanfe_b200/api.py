@@ -32,7 +32,7 @@ _VCOV = {"iid": capi.VCOV_IID, "hc1": capi.VCOV_HC1, "cluster": capi.VCOV_CLUSTE
 
 def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strategy="auto", weights=None,
            demean_tol=1e-6, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None,
-           backend="polars", con=None, device=None, profile=False) -> LeanFEResult:
+           backend="polars", con=None, device=None, profile=False, local_fe=None) -> LeanFEResult:
     """Fast fixed-effects regression; drop-in for ``leanfe.leanfe`` with the compute on a B200.
 
     ``backend`` accepts "polars" (the backend this package replaces), "b200" or "cuda"; "duckdb" is a
@@ -44,7 +44,7 @@ def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strateg
         return leanfe_b200(data=data, y_col=y_col, x_cols=x_cols, fe_cols=fe_cols, formula=formula,
                            strategy=strategy, weights=weights, demean_tol=demean_tol, max_iter=max_iter, vcov=vcov,
                            cluster_cols=cluster_cols, ssc=ssc, sample_frac=sample_frac, device=device,
-                           profile=profile)
+                           profile=profile, local_fe=local_fe)
     if backend == "duckdb":
         raise ValueError("backend='duckdb' is not provided by leanfe_b200 (out of scope: it replaces the Polars "
                          "backend's compute); use backend='polars'")
