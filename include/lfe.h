@@ -136,6 +136,19 @@ int lfe_demean(lfe_handle h, double* const* cols, int C, const int32_t* const* c
                int* iterations_out /*[host]*/, double* max_mean_out /*[host]*/,
                int* converged_out /*[host]*/, void* stream);
 
+/* The same operator in two steps.  The plan holds everything that depends on the code columns only (the
+ * per-FE sorted entry lists and group sizes), so it can be built while the data columns are still being
+ * uploaded, and re-run for several column sets on one panel.  codes / weights must stay valid and
+ * unchanged until lfe_demean_plan_destroy.  lfe_demean == create + run + destroy.                    */
+typedef struct lfe_plan* lfe_plan_t;
+int lfe_demean_plan_create(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
+                           int64_t n, const double* weights, int local_fe, lfe_plan_t* plan_out,
+                           void* stream);
+int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, int C, const int* fe_order,
+                        double tol, int max_iter, int min_iter, int flags, int* iterations_out /*[host]*/,
+                        double* max_mean_out /*[host]*/, int* converged_out /*[host]*/, void* stream);
+int lfe_demean_plan_destroy(lfe_handle h, lfe_plan_t plan);
+
 /* ---- (4) Gram + solve --------------------------------------------------------------------------
  * Replaces: X = [1 | X~], X'X, X'y  polars_impl.py:166-209 (weighted: sqrt(w) scaling :201-206).
  * Z = [1 | cols[0] .. cols[C-1]] when add_intercept else [cols]; gram_out (device, P x P row-major,

@@ -17,7 +17,7 @@ import torch
 from . import _capi as capi
 from .engine import Engine, get_engine
 from .formula import parse_formula
-from .frontend import Frame, KeyColumn, resolve_reference, to_device_f64, to_device_key
+from .frontend import Frame, KeyColumn, Uploader, resolve_reference, to_device_f64, to_device_key
 from .result import LeanFEResult
 from .strategy import MAX_FE_LEVELS, determine_strategy
 
@@ -100,14 +100,6 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         eng.set_profiling(True)
         eng.reset_timers()
     frame = Frame(data, needed)
-    numeric: dict[str, torch.Tensor] = {}
-    keys: dict[str, KeyColumn] = {}
-
-    def num(name):
-        if name not in numeric:
-            numeric[name] = to_device_f64(eng, frame.column(name))
-        return numeric[name]
-
     dist = eng.world > 1
     if dist:
         if local_fe is None or local_fe not in fe_cols:
@@ -116,40 +108,62 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             raise NotImplementedError("multi-GPU fits support strategy='alt_proj' / 'demean' (pass it explicitly)")
         if sample_frac is not None:
             raise NotImplementedError("sample_frac is not supported in multi-GPU fits")
+        if cluster_cols and len(cluster_cols) > 1:
+            raise NotImplementedError("multi-way clustering is single-GPU only")
+
+    # every H2D copy is enqueued now, ids first: the id-only work below overlaps the fp64 uploads
+    key_first = fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions] + [v for v, _ in factor_vars]
+    up = Uploader(eng, frame, key_first + ([weights] if weights is not None else []) + needed)
+    numeric: dict[str, torch.Tensor] = {}
+    keys: dict[str, KeyColumn] = {}
+
+    def num(name):
+        if name not in numeric:
+            numeric[name] = to_device_f64(eng, up.get(name))
+        return numeric[name]
 
     def key(name, labels=False):
         if name not in keys or (labels and keys[name].labels is None):
             # multi-GPU: every key column except the shard key needs ONE code space shared by all ranks
-            keys[name] = to_device_key(eng, frame.column(name), want_labels=labels,
-                                       global_codes=dist and name != local_fe)
+            keys[name] = to_device_key(eng, up.get(name), want_labels=labels, global_codes=dist and name != local_fe)
         return keys[name]
-
-    y = num(y_col)
-    X = [num(c) for c in x_cols]
-    w = num(weights) if weights is not None else None
-
-    # interactions then factors (polars_impl.py:350-365); labels come from the original values
-    for var, factor, ref in interactions:
-        kc = key(factor, labels=True)
-        ref_cat = resolve_reference(kc.labels, ref, factor)
-        base = num(var)
-        for j, cat in enumerate(kc.labels):
-            if cat == ref_cat:
-                continue
-            X.append(base * (kc.codes == j))
-            x_cols.append(f"{var}_{cat}")
-    for var, ref in factor_vars:
-        kc = key(var, labels=True)
-        ref_cat = resolve_reference(kc.labels, ref, var)
-        for j, cat in enumerate(kc.labels):
-            if cat == ref_cat:
-                continue
-            X.append((kc.codes == j).to(torch.float64))
-            x_cols.append(f"{var}_{cat}")
 
     fe_keys = [key(c) for c in fe_cols]
     cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
-    n0 = y.numel()
+    base_x = list(x_cols)
+
+    def columns():
+        """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
+        y_ = num(y_col)
+        X_ = [num(c) for c in base_x]
+        names = list(base_x)
+        w_ = num(weights) if weights is not None else None
+        # interactions then factors (polars_impl.py:350-365); labels come from the original values
+        for var, factor, ref in interactions:
+            kc = key(factor, labels=True)
+            ref_cat = resolve_reference(kc.labels, ref, factor)
+            base = num(var)
+            for j, cat in enumerate(kc.labels):
+                if cat != ref_cat:
+                    X_.append(base * (kc.codes == j))
+                    names.append(f"{var}_{cat}")
+        for var, ref in factor_vars:
+            kc = key(var, labels=True)
+            ref_cat = resolve_reference(kc.labels, ref, var)
+            for j, cat in enumerate(kc.labels):
+                if cat != ref_cat:
+                    X_.append((kc.codes == j).to(torch.float64))
+                    names.append(f"{var}_{cat}")
+        return y_, X_, names, w_
+
+    cols_cache = []
+
+    def get_columns():
+        if not cols_cache:
+            cols_cache.append(columns())
+        return cols_cache[0]
+
+    n0 = fe_keys[0].codes.numel() if fe_keys else get_columns()[0].numel()
 
     if sample_frac is not None:
         # the reference samples with Polars' RNG (seed 42, polars_impl.py:359-360); not reproducible without
@@ -158,8 +172,9 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         g.manual_seed(42)
         m = int(n0 * sample_frac)
         idx = torch.randperm(n0, generator=g, device=eng.device)[:m].sort().values
-        y, X = y[idx].contiguous(), [c[idx].contiguous() for c in X]
-        w = w[idx].contiguous() if w is not None else None
+        y, X, names, w = get_columns()
+        cols_cache[0] = (y[idx].contiguous(), [c[idx].contiguous() for c in X], names,
+                         w[idx].contiguous() if w is not None else None)
         fe_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in fe_keys]
         cl_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in cl_keys]
         n0 = m
@@ -169,13 +184,13 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     if strategy == "auto":
         def ratio():
             # distinct rows over set(x_cols + fe_cols) / N   (compress.py:232-253)
-            names = list(dict.fromkeys(x_cols + fe_cols))
+            _, X, names, _ = get_columns()
             kcs = []
-            for nm in names:
+            for nm in dict.fromkeys(names + fe_cols):
                 if nm in fe_cols:
                     kcs.append(fe_keys[fe_cols.index(nm)])
                 else:
-                    c_, G_, _ = eng.factorize(X[x_cols.index(nm)])
+                    c_, G_, _ = eng.factorize(X[names.index(nm)])
                     kcs.append(KeyColumn(c_, G_))
             if not kcs:
                 return 1.0
@@ -194,17 +209,17 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
                 strategy = "alt_proj"
             else:
                 est_ratio = ratio()
-                strategy = determine_strategy(vcov, False, fe_card, MAX_FE_LEVELS, n0, len(x_cols), est_ratio)
+                strategy = determine_strategy(vcov, False, fe_card, MAX_FE_LEVELS, n0, len(get_columns()[2]), est_ratio)
 
     if strategy == "compress":
+        y, X, x_cols, w = get_columns()
         res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
         res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
     else:
         lf = fe_cols.index(local_fe) if dist else -1
         cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
-        if dist and cluster_cols and len(cluster_cols) > 1:
-            raise NotImplementedError("multi-way clustering is single-GPU only")
-        res = _fit_fwl(eng, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, demean_tol,
+        w_early = num(weights) if weights is not None else None
+        res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
                        max_iter, formula, est_ratio, lf, cl_local)
     if profile:
         torch.cuda.synchronize(eng.device)
@@ -214,46 +229,56 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
 
 # ------------------------------------------------------------------------------------------------
-def _fit_fwl(eng: Engine, strategy, y, X, x_cols, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
+def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
              formula, est_ratio, local_fe=-1, cl_local=False) -> LeanFEResult:
-    """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression."""
-    k = len(X)
+    """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression.
+
+    ``get_columns()`` -> (y, X, names, w) is called as late as possible: the singleton test and the demean plan
+    (entry-list sorts) need only the ids and run while the fp64 columns are still being uploaded.
+    """
     F = len(fe_keys)
     if strategy == "demean" and F != 1:
         raise ValueError("Strategy 'demean' requires exactly one FE column.")
     if strategy == "alt_proj" and F == 0:
         raise ValueError("Strategy 'alt_proj' requires FE-cols. Use strategy='ols' instead for OLS without FE.")
-    cols = [y] + list(X)
     cl_codes = [c.codes for c in cl_keys]
     iterations, converged, fe_dims, absorbed = 0, None, None, 0
     if strategy != "ols":
         codes = [f.codes for f in fe_keys]
         Gs = [f.n_groups for f in fe_keys]
+        order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
         # singleton filter: one pass, all FEs (polars_impl.py:478-482)
         keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe)
-        n_obs_global = eng.last_n_keep_global
-        owned = False
-        if n_keep < y.numel():
-            f_in = cols + ([w] if w is not None else [])
+        n_obs = eng.last_n_keep_global
+        if n_keep < codes[0].numel():
+            y, X, x_cols, w = get_columns()
+            k = len(X)
+            f_in = [y] + X + ([w] if w is not None else [])
             extra = [c for c in cl_codes if not any(c is f for f in codes)]     # a cluster column may be an FE
             f_out, i_out = eng.compact(keep, n_keep, f_in, codes + extra)
             cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
             new_of = {id(o): n_ for o, n_ in zip(codes + extra, i_out)}
             codes, cl_codes = i_out[:F], [new_of[id(c)] for c in cl_codes]
-            owned = True
-        # rows are never permuted: lfe_demean sorts only the int32 code columns (one entry list per FE)
-        if not owned:
-            cols = [c.clone() for c in cols]          # lfe_demean works in place; never touch caller data
-        order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
+            plan = eng.demean_plan(codes, Gs, w, local_fe)
+        else:
+            # rows are never permuted: the plan sorts only the int32 code columns (one entry list per FE)
+            plan = eng.demean_plan(codes, Gs, w, local_fe)
+            y, X, x_cols, w = get_columns()
+            k = len(X)
+            cols = [c.clone() for c in [y] + X]       # lfe_demean works in place; never touch caller data
+        del keep
         if strategy == "demean":
-            iterations, _, _ = eng.demean(cols, codes, Gs, order, w, tol, 1, 2, local_fe)
+            plan.run(cols, order, tol, 1, 2)
             iterations, converged = 1, True
             absorbed = fe_dims[0] - 1
         else:
-            iterations, _, converged = eng.demean(cols, codes, Gs, order, w, tol, max_iter, 3, local_fe)
+            iterations, _, converged = plan.run(cols, order, tol, max_iter, 3)
             absorbed = sum(fe_dims) - F
-        n_obs = n_obs_global
+        plan.close()
     else:
+        y, X, x_cols, w = get_columns()
+        k = len(X)
+        cols = [y] + list(X)
         n_obs = cols[0].numel()
     if vkind == capi.VCOV_CLUSTER and cl_local:
         vkind |= capi.VCOV_CLUSTER_LOCAL

@@ -17,6 +17,8 @@
 // thread-local run compression, a warp-shuffle segmented scan, and one RED.ADD.F64 per (warp, group)
 // for groups that straddle warps.  After convergence one streaming pass applies the tables to the
 // columns in place.
+#include <memory>
+
 #include "common.cuh"
 #include "segreduce.cuh"
 
@@ -312,30 +314,30 @@ static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const Apply
   h->n_launches += 1;
 }
 
-void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* codes, const int64_t* n_groups,
-                 const int* fe_order, int F, int64_t n, const double* weights, double tol, int max_iter, int min_iter,
-                 int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
-                 cudaStream_t s) {
-  const bool strict_check = (flags & LFE_DEMEAN_STRICT_CHECK) != 0;
+// The column-independent part of a fit: entry lists and group sizes.  Built from the code columns alone, so
+// the host can build it while the data columns are still in flight over PCIe, and reuse it for several
+// outcome/regressor sets on the same panel.
+struct lfe_plan {
+  int F = 0;
+  int64_t n = 0;
+  bool weighted = false;
+  int local_fe = -1;
+  const int32_t* codes[LFE_MAX_FE] = {nullptr};
+  const double* weights = nullptr;
+  std::vector<FEState> st;
+};
+
+lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
+                             const double* weights, int local_fe, cudaStream_t s) {
   LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_demean: F=%d out of range [1,%d]", F, LFE_MAX_FE);
-  LFE_REQUIRE(C >= 1, "lfe_demean: C must be >= 1");
   LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_demean: n out of range");
-  LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
-  {
-    bool seen[LFE_MAX_FE] = {false};
-    for (int j = 0; j < F; ++j) {
-      LFE_REQUIRE(fe_order[j] >= 0 && fe_order[j] < F && !seen[fe_order[j]], "lfe_demean: fe_order is not a permutation");
-      seen[fe_order[j]] = true;
-    }
-  }
   const bool weighted = weights != nullptr;
   const bool dist = h->world > 1;
-  *iterations_out = 0;
-  if (max_mean_out) *max_mean_out = 0.0;
-  if (converged_out) *converged_out = 0;
-
-  std::vector<FEState> st(F);
-  // ---- setup: per-FE sorted entry lists, counts, S0 --------------------------------------------
+  std::unique_ptr<lfe_plan> plan(new lfe_plan());
+  plan->F = F; plan->n = n; plan->weighted = weighted; plan->local_fe = local_fe; plan->weights = weights;
+  for (int j = 0; j < F; ++j) plan->codes[j] = codes[j];
+  plan->st.resize(F);
+  std::vector<FEState>& st = plan->st;
   {
     PhaseTimer t(h, s, 5);
     // Entry lists.  The highest-cardinality FE ("big") is sorted first; every other FE is then sorted
@@ -400,14 +402,10 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
         }
       }
     }
+    // group sizes: unweighted counts (and sum of weights per group when weighted)
     for (int j = 0; j < F; ++j) {
       FEState& S = st[j];
-      size_t tab = (size_t)S.G * C;
-      S.alpha.alloc(tab, s); S.S0.alloc(tab, s); S.acc.alloc(tab, s); S.nsum.alloc(S.G, s);
-      S.alpha.zero(); S.S0.zero(); S.acc.zero();
-      S.acc_chk.alloc(S.G, s);
-      S.acc_chk.zero();
-      // unweighted counts
+      S.nsum.alloc(S.G, s);
       {
         DevBuf<uint32_t> c32(S.G, s);
         prim_histogram(h, codes[j], n, S.G, c32, s);
@@ -415,6 +413,67 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
         if (weighted) S.cnt_buf.alloc(S.G, s);
         prim_u32_to_f64(h, c32, S.G, dst, s);
       }
+      if (weighted) {
+        S.nsum.zero();
+        ColPtrs cw; cw.col[0] = weights;
+        launch_groupsum<false>(h, 1, codes[j], S.G, cw, nullptr, n, S.nsum, 1, 0, s);
+        S.cnt = S.cnt_buf;
+      } else {
+        S.cnt = S.nsum;
+      }
+      if (dist && j != local_fe) {
+        PhaseTimer tc(h, s, 13);
+        comm_allreduce(h, S.nsum, S.G, 0, s);
+        if (weighted) comm_allreduce(h, S.cnt_buf, S.G, 0, s);
+      }
+    }
+  }
+  return plan.release();
+}
+
+void demean_plan_destroy(lfe_plan* plan) { delete plan; }
+
+void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, const int* fe_order, double tol,
+                     int max_iter, int min_iter, int flags, int* iterations_out, double* max_mean_out,
+                     int* converged_out, cudaStream_t s) {
+  const bool strict_check = (flags & LFE_DEMEAN_STRICT_CHECK) != 0;
+  const int F = plan->F;
+  const int64_t n = plan->n;
+  const bool weighted = plan->weighted;
+  const int local_fe = plan->local_fe;
+  const double* weights = plan->weights;
+  const int32_t* const* codes = plan->codes;
+  std::vector<FEState>& st = plan->st;
+  LFE_REQUIRE(C >= 1, "lfe_demean: C must be >= 1");
+  LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
+  {
+    bool seen[LFE_MAX_FE] = {false};
+    for (int j = 0; j < F; ++j) {
+      LFE_REQUIRE(fe_order[j] >= 0 && fe_order[j] < F && !seen[fe_order[j]], "lfe_demean: fe_order is not a permutation");
+      seen[fe_order[j]] = true;
+    }
+  }
+  const bool dist = h->world > 1;
+  *iterations_out = 0;
+  if (max_mean_out) *max_mean_out = 0.0;
+  if (converged_out) *converged_out = 0;
+  // release the per-run tables when this call returns, whatever happens
+  struct TableGuard {
+    std::vector<FEState>& st;
+    ~TableGuard() {
+      for (auto& S : st) { S.alpha.release(); S.S0.release(); S.acc.release(); S.acc_chk.release(); S.S0u_buf.release(); }
+    }
+  } guard{st};
+  // ---- S0: the only pass over the columns before the final apply -----------------------------------
+  {
+    PhaseTimer t(h, s, 5);
+    for (int j = 0; j < F; ++j) {
+      FEState& S = st[j];
+      size_t tab = (size_t)S.G * C;
+      S.alpha.alloc(tab, s); S.S0.alloc(tab, s); S.acc.alloc(tab, s);
+      S.alpha.zero(); S.S0.zero(); S.acc.zero();
+      S.acc_chk.alloc(S.G, s);
+      S.acc_chk.zero();
       // S0 (weighted sums of every column), column batches of <= PJ_MAXNC
       for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
         int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
@@ -424,26 +483,19 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
         else launch_groupsum<false>(h, nc, codes[j], S.G, cp, nullptr, n, S.S0, C, c0, s);
       }
       if (weighted) {
-        // n_j = sum of weights per group; unweighted y sums for the convergence check
-        S.nsum.zero();
-        ColPtrs cw; cw.col[0] = weights;
-        launch_groupsum<false>(h, 1, codes[j], S.G, cw, nullptr, n, S.nsum, 1, 0, s);
+        // unweighted y sums for the convergence check (polars_impl.py:513 ignores the weights)
         S.S0u_buf.alloc(S.G, s);
         S.S0u_buf.zero();
         ColPtrs cy; cy.col[0] = cols[0];
         launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
-        S.cnt = S.cnt_buf; S.S0u = S.S0u_buf; S.ld_s0u = 1;
+        S.S0u = S.S0u_buf; S.ld_s0u = 1;
       } else {
-        S.cnt = S.nsum; S.S0u = S.S0; S.ld_s0u = C;
+        S.S0u = S.S0; S.ld_s0u = C;
       }
       if (dist && j != local_fe) {
         PhaseTimer tc(h, s, 13);
         comm_allreduce(h, S.S0, (int64_t)tab, 0, s);
-        comm_allreduce(h, S.nsum, S.G, 0, s);
-        if (weighted) {
-          comm_allreduce(h, S.cnt_buf, S.G, 0, s);
-          comm_allreduce(h, S.S0u_buf, S.G, 0, s);
-        }
+        if (weighted) comm_allreduce(h, S.S0u_buf, S.G, 0, s);
       }
     }
   }
@@ -545,4 +597,13 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
   *iterations_out = iterations;
   if (max_mean_out) *max_mean_out = max_mean;
   if (converged_out) *converged_out = converged ? 1 : 0;
+}
+
+void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* codes, const int64_t* n_groups,
+                 const int* fe_order, int F, int64_t n, const double* weights, double tol, int max_iter, int min_iter,
+                 int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
+                 cudaStream_t s) {
+  std::unique_ptr<lfe_plan> plan(demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, s));
+  demean_plan_run(h, plan.get(), cols, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
+                  converged_out, s);
 }

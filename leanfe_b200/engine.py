@@ -57,6 +57,12 @@ class Engine:
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def copy_stream(self):
+        """One persistent side stream for host->device copies (overlapped with the id-only compute)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
     def empty(self, n, dtype):
         return torch.empty(int(n), dtype=dtype, device=self.device)
 
@@ -183,6 +189,11 @@ class Engine:
                                        C.byref(cv), self.stream))
         return int(it.value), float(mm.value), bool(cv.value)
 
+    def demean_plan(self, codes: list[torch.Tensor], n_groups: list[int], weights: torch.Tensor | None = None,
+                    local_fe: int = -1) -> "DemeanPlan":
+        """Column-independent part of lfe_demean (entry lists, group sizes); see ``DemeanPlan.run``."""
+        return DemeanPlan(self, codes, n_groups, weights, local_fe)
+
     # -- (4) gram / solve ---------------------------------------------------------------------
     def gram(self, cols: list[torch.Tensor], weights: torch.Tensor | None = None, add_intercept: bool = True):
         self._check_dev(*cols, weights)
@@ -304,6 +315,49 @@ class Engine:
     def allreduce(self, t: torch.Tensor):
         capi.check(self.lib.lfe_allreduce_f64(self.h, self._p(t), t.numel(), self.stream))
         return t
+
+
+class DemeanPlan:
+    """lfe_demean_plan_*: built from the code columns only, runnable on any number of column sets."""
+
+    def __init__(self, eng: Engine, codes, n_groups, weights, local_fe):
+        eng._check_dev(*codes, weights)
+        self.eng, self.codes, self.weights, self.n_groups = eng, list(codes), weights, list(n_groups)   # keep alive
+        self.n = codes[0].numel()
+        for t in codes:
+            if t.dtype != torch.int32 or t.numel() != self.n:
+                raise ValueError("codes must be int32 tensors of equal length")
+        p = C.c_void_p()
+        capi.check(eng.lib.lfe_demean_plan_create(eng.h, capi.ptr_array([t.data_ptr() for t in codes]),
+                                                  capi.i64_array(n_groups), len(codes), self.n, eng._p(weights),
+                                                  int(local_fe), C.byref(p), eng.stream))
+        self.p = p
+
+    def run(self, cols: list[torch.Tensor], fe_order: list[int], tol: float = 1e-6, max_iter: int = 50,
+            min_iter: int = 3, strict_check: bool = False):
+        """In place on ``cols`` (cols[0] = y).  -> (iterations, max_mean, converged)"""
+        eng = self.eng
+        eng._check_dev(*cols)
+        for t in cols:
+            if t.dtype != torch.float64 or t.numel() != self.n:
+                raise ValueError("demean columns must be float64 with one value per plan row")
+        it, mm, cv = C.c_int(0), C.c_double(0.0), C.c_int(0)
+        capi.check(eng.lib.lfe_demean_plan_run(eng.h, self.p, capi.ptr_array([t.data_ptr() for t in cols]), len(cols),
+                                               capi.i32_array(fe_order), float(tol), int(max_iter), int(min_iter),
+                                               1 if strict_check else 0, C.byref(it), C.byref(mm), C.byref(cv),
+                                               eng.stream))
+        return int(it.value), float(mm.value), bool(cv.value)
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.eng.lib.lfe_demean_plan_destroy(self.eng.h, self.p)
+            self.p = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _ENGINES: dict[int, Engine] = {}

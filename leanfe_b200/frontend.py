@@ -70,6 +70,70 @@ def _arrow_to_numpy(chunked):
     return arr.to_numpy(zero_copy_only=False)
 
 
+class Uploader:
+    """All host->device copies of a fit, enqueued up front on a dedicated copy stream.
+
+    Key columns go first so that factorisation, the singleton test and the entry-list sorts (which need only
+    the ids) run while the fp64 columns are still crossing PCIe; the compute stream waits on a per-column
+    event right before a column's first use.  With pinned host tensors the copies are truly asynchronous;
+    with pageable memory the driver stages them synchronously and this degrades to the plain ordering.
+    """
+
+    def __init__(self, eng: Engine, frame: Frame, names: list[str]):
+        self.eng, self.frame = eng, frame
+        self.compute = torch.cuda.current_stream(eng.device)
+        self.copy = None
+        self.dev: dict[str, torch.Tensor] = {}
+        self.events: dict[str, torch.cuda.Event] = {}
+        self._host_refs: list = []
+        pending = []
+        for name in dict.fromkeys(names):
+            col = frame.column(name)
+            if isinstance(col, torch.Tensor):
+                t = col
+            elif _is_stringlike(col):
+                continue                                   # dictionary-encoded on the host at first use
+            else:
+                a = np.asarray(col)
+                if a.dtype == np.bool_:
+                    a = a.astype(np.uint8)
+                elif a.dtype in (np.int8, np.int16, np.uint16):
+                    a = a.astype(np.int32)
+                elif a.dtype == np.float16:
+                    a = a.astype(np.float32)
+                if not a.flags.writeable:
+                    a = a.copy()
+                t = torch.from_numpy(np.ascontiguousarray(a))
+            if t.is_cuda:
+                self.dev[name] = t.contiguous()
+                continue
+            # destination allocated on the COMPUTE stream (so the caching allocator reuses the previous fit's
+            # blocks instead of growing a per-copy-stream pool), filled on the engine's one copy stream
+            t = t.contiguous()
+            d = torch.empty(t.shape, dtype=t.dtype, device=eng.device)
+            pending.append((name, t, d))
+        if pending:
+            self.copy = eng.copy_stream()
+            self.copy.wait_stream(self.compute)
+            with torch.cuda.stream(self.copy):
+                for name, t, d in pending:
+                    d.copy_(t, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy)
+                    d.record_stream(self.copy)
+                    self.dev[name], self.events[name] = d, ev
+                    self._host_refs.append(t)              # keep the source alive until the async copy ran
+
+    def get(self, name: str):
+        """Device tensor of an uploaded column (compute stream ordered after its copy), else the host column."""
+        if name in self.dev:
+            ev = self.events.pop(name, None)
+            if ev is not None:
+                self.compute.wait_event(ev)
+            return self.dev[name]
+        return self.frame.column(name)
+
+
 @dataclass
 class KeyColumn:
     """A group-key column on the device: dense int32 codes + cardinality (+ labels when needed)."""
