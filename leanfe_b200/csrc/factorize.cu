@@ -5,6 +5,8 @@
 // Keys are first mapped to an order-preserving uint64 image; if their range is small (the common
 // case for panel ids) a direct-address presence table + scan gives the ranks in three streaming
 // passes; otherwise a stable LSD radix argsort of (key - min) does.
+#include <climits>
+
 #include "common.cuh"
 
 void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);  // api.cu
@@ -260,9 +262,81 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
   return G;
 }
 
+// ---- float keys that are really small integers (dummies, counts, years stored as double) -------------
+// flags[0] |= 1 if any value is non-integral / non-finite / outside +-2^52 ; mm = {min, max} as int64
+__global__ void __launch_bounds__(256) k_f64_integral_range(const double* __restrict__ v, int64_t n,
+                                                            int* __restrict__ bad, long long* __restrict__ mm) {
+  long long lo = LLONG_MAX, hi = LLONG_MIN;
+  int b = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double x = __ldcs(v + i);
+    if (!(fabs(x) < 4503599627370496.0) || x != rint(x)) { b = 1; continue; }
+    long long q = (long long)x;
+    lo = q < lo ? q : lo;
+    hi = q > hi ? q : hi;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    long long a = __shfl_xor_sync(0xffffffffu, lo, d), c = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo;
+    hi = c > hi ? c : hi;
+    b |= __shfl_xor_sync(0xffffffffu, b, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (b) atomicOr(bad, 1);
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+__global__ void __launch_bounds__(256) k_f64_to_i64(const double* __restrict__ v, int64_t n, long long* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (long long)__ldcs(v + i);     // -0.0 -> 0: the canonical form
+}
+__global__ void __launch_bounds__(256) k_i64_to_f64(const long long* __restrict__ v, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)v[i];
+}
+
+// Integer-valued doubles with a small range take the direct-address path instead of a 64-bit radix sort.
+static bool factorize_f64_as_int(lfe_ctx* h, const double* keys, int64_t n, int order, int32_t* codes, double* uniques,
+                                 int64_t uniques_cap, cudaStream_t s, int64_t* G_out) {
+  if (n <= 0 || (order & LFE_ORDER_GLOBAL)) return false;
+  DevBuf<int> bad(1, s);
+  DevBuf<long long> mm(2, s);
+  bad.zero();
+  long long init[2] = {LLONG_MAX, LLONG_MIN};
+  CUDA_CHECK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  k_f64_integral_range<<<blocks, 256, 0, s>>>(keys, n, bad, mm);
+  KERNEL_CHECK();
+  int hb = 0;
+  long long hmm[2];
+  CUDA_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  h->n_launches += 1;
+  if (hb || hmm[1] < hmm[0] || (unsigned long long)(hmm[1] - hmm[0]) >= (1ull << 24)) return false;
+  DevBuf<long long> ik(n, s), iu;
+  k_f64_to_i64<<<blocks, 256, 0, s>>>(keys, n, ik);
+  KERNEL_CHECK();
+  if (uniques) iu.alloc((size_t)(hmm[1] - hmm[0] + 1), s);
+  int64_t G = factorize_impl<LFE_I64>(h, ik.p, n, order, codes, uniques ? iu.p : nullptr, hmm[1] - hmm[0] + 1, s);
+  if (uniques && G <= uniques_cap) {
+    k_i64_to_f64<<<launch_blocks(h, ceil_div64(G, 256), 8), 256, 0, s>>>(iu.p, G, uniques);
+    KERNEL_CHECK();
+  }
+  h->n_launches += 2;
+  *G_out = G;
+  return true;
+}
+
 int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
                            void* uniques, int64_t uniques_cap, cudaStream_t s) {
   PhaseTimer t(h, s, 0);
+  if (key_dtype == LFE_F64) {
+    int64_t G = 0;
+    if (factorize_f64_as_int(h, (const double*)keys, n, order, codes, (double*)uniques, uniques_cap, s, &G)) return G;
+  }
   switch (key_dtype) {
     case LFE_I32: return factorize_impl<LFE_I32>(h, keys, n, order, codes, uniques, uniques_cap, s);
     case LFE_I64: return factorize_impl<LFE_I64>(h, keys, n, order, codes, uniques, uniques_cap, s);

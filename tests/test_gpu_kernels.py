@@ -60,6 +60,21 @@ def test_factorize_float_keys_canonical(eng):
     assert not np.signbit(uniq.cpu().numpy()[exp_uniq == 0.0]).any()     # -0.0 was canonicalised to +0.0
 
 
+def test_factorize_integer_valued_doubles_take_the_direct_path(eng):
+    rng = np.random.default_rng(22)
+    v = rng.integers(-3, 40, 120_000).astype(np.float64)
+    v[::11] = -0.0
+    codes, G, uniq = eng.factorize(dev(v), want_uniques=True)
+    exp_codes, exp_uniq, _ = O.codes_sorted(v)
+    assert G == len(exp_uniq)
+    np.testing.assert_array_equal(codes.cpu().numpy(), exp_codes)
+    np.testing.assert_array_equal(uniq.cpu().numpy(), exp_uniq)
+    d = (rng.random(50_000) < 0.3).astype(np.float64)                      # a 0/1 dummy stored as double
+    codes, G, uniq = eng.factorize(dev(d), want_uniques=True)
+    assert G == 2 and uniq.cpu().tolist() == [0.0, 1.0]
+    np.testing.assert_array_equal(codes.cpu().numpy(), d.astype(np.int32))
+
+
 def test_factorize_first_appearance(eng):
     rng = np.random.default_rng(3)
     v = rng.integers(0, 3000, 100_000) * 11 - 500
