@@ -25,52 +25,85 @@
 void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);  // api.cu
 
 // acc[key][acc_col0 + c] += w * sum_k alpha_k[code_k][col0 + c]    over the FE-sorted entry list
-template <int NC, bool WEIGHTED>
-__global__ void __launch_bounds__(PJ_T) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
-                                               const double* __restrict__ w, int64_t n, int ldc, int col0,
-                                               double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes) {
-  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
-  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
-  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
-    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
-    int k[PJ_I];
-    load4_i32(key, base, n, vec_codes, k);
-    double v[PJ_I][NC];
+constexpr int PJ_NB = 2;  // sub-batches of PJ_I entries per thread: 8 consecutive entries, one warp scan
+
+// One sub-batch: keys + gathered/summed rows of the other FEs' tables.  FULL = all 4 entries exist (no bounds
+// or validity branches, so the compiler hoists all 128-bit gathers ahead of the first use).
+template <int NC, bool WEIGHTED, bool FULL>
+__device__ __forceinline__ void proj_batch(const int32_t* __restrict__ key, const ProjOthers& oth,
+                                           const double* const tabs[LFE_MAX_FE], const double* __restrict__ w,
+                                           int64_t base, int64_t n, int ldc, int col0, bool vec_codes, bool vec2,
+                                           int k[PJ_I], double v[PJ_I][NC]) {
+  load4_i32(key, base, n, vec_codes && FULL, k);
 #pragma unroll
-    for (int e = 0; e < PJ_I; ++e)
+  for (int e = 0; e < PJ_I; ++e)
 #pragma unroll
-      for (int c = 0; c < NC; ++c) v[e][c] = 0.0;
-    for (int o = 0; o < oth.n; ++o) {
-      int oc[PJ_I];
-      load4_i32(oth.code[o], base, n, vec_codes, oc);
-      const double* __restrict__ tab = oth.alpha[o] + col0;
+    for (int c = 0; c < NC; ++c) v[e][c] = 0.0;
+  for (int o = 0; o < oth.n; ++o) {
+    int oc[PJ_I];
+    load4_i32(oth.code[o], base, n, vec_codes && FULL, oc);
+    const double* tab = tabs[o] + col0;   // global (L2-resident) or the CTA's shared-memory copy
 #pragma unroll
-      for (int e = 0; e < PJ_I; ++e) {
-        if (oc[e] >= 0) {
-          const double* row = tab + (size_t)oc[e] * ldc;
-          if (vec2) {
+    for (int e = 0; e < PJ_I; ++e) {
+      if (FULL || oc[e] >= 0) {
+        const double* row = tab + (size_t)oc[e] * ldc;
+        if (vec2) {
 #pragma unroll
-            for (int c = 0; c < NC / 2; ++c) {
-              double2 t = __ldg(reinterpret_cast<const double2*>(row) + c);
-              v[e][2 * c] += t.x;
-              v[e][2 * c + 1] += t.y;
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) v[e][c] += __ldg(row + c);
+          for (int c = 0; c < NC / 2; ++c) {
+            double2 t = *(reinterpret_cast<const double2*>(row) + c);
+            v[e][2 * c] += t.x;
+            v[e][2 * c + 1] += t.y;
           }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) v[e][c] += row[c];
         }
       }
     }
-    if (WEIGHTED) {
+  }
+  if (WEIGHTED) {
 #pragma unroll
-      for (int e = 0; e < PJ_I; ++e) {
-        double we = (base + e < n) ? __ldcs(w + base + e) : 0.0;
+    for (int e = 0; e < PJ_I; ++e) {
+      double we = (FULL || base + e < n) ? __ldcs(w + base + e) : 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[e][c] *= we;
+      for (int c = 0; c < NC; ++c) v[e][c] *= we;
+    }
+  }
+}
+
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
+                                               const double* __restrict__ w, int64_t n, int ldc, int col0,
+                                               double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes) {
+  constexpr int PER_THREAD = PJ_I * PJ_NB;
+  extern __shared__ double sm_tabs[];
+  const double* tabs[LFE_MAX_FE];
+  stage_tables(oth, ldc, sm_tabs, tabs);
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PER_THREAD);
+  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t tbase = (ch * PJ_T + threadIdx.x) * PER_THREAD;
+    int cur = -1;
+    double run[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) run[c] = 0.0;
+    if (tbase + PER_THREAD <= n) {
+#pragma unroll 1
+      for (int b = 0; b < PJ_NB; ++b) {
+        int k[PJ_I];
+        double v[PJ_I][NC];
+        proj_batch<NC, WEIGHTED, true>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, k, v);
+        run_fold<NC>(cur, run, k, v, acc, ld_acc, acc_col0);
+      }
+    } else {
+      for (int b = 0; b < PJ_NB; ++b) {
+        int k[PJ_I];
+        double v[PJ_I][NC];
+        proj_batch<NC, WEIGHTED, false>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, k, v);
+        run_fold<NC>(cur, run, k, v, acc, ld_acc, acc_col0);
       }
     }
-    segmented_flush<NC>(k, v, acc, ld_acc, acc_col0);
+    warp_flush<NC>(cur, run, acc, ld_acc, acc_col0);
   }
 }
 
@@ -132,16 +165,18 @@ __global__ void __launch_bounds__(256) k_binsum_smem(const int32_t* __restrict__
 }
 
 // delta_max (nullable): max |alpha_new - alpha_old| = largest weighted group mean of the residual just removed
-__global__ void __launch_bounds__(256) k_finalize(double* __restrict__ alpha, double* __restrict__ acc,
+// alpha_out may alias alpha_in (in place) or be a staging table (speculative projection, see the loop);
+// delta_col < 0: the max runs over all columns, else over that column only (the y-only stopping test).
+__global__ void __launch_bounds__(256) k_finalize(const double* alpha_in, double* alpha_out, double* __restrict__ acc,
                                                   const double* __restrict__ S0, const double* __restrict__ nsum,
-                                                  int64_t G, int C, double* __restrict__ delta_max) {
+                                                  int64_t G, int C, double* __restrict__ delta_max, int delta_col) {
   const int64_t tot = G * C;
   double m = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
     double nn = nsum[i / C];
     double a = nn > 0.0 ? (S0[i] - acc[i]) / nn : 0.0;
-    if (delta_max) m = fmax(m, fabs(a - alpha[i]));
-    alpha[i] = a;
+    if (delta_max && nn > 0.0 && (delta_col < 0 || (int)(i % C) == delta_col)) m = fmax(m, fabs(a - alpha_in[i]));
+    alpha_out[i] = a;
     acc[i] = 0.0;
   }
   if (delta_max) {
@@ -175,30 +210,29 @@ __global__ void __launch_bounds__(256) k_u32_to_f64(const uint32_t* __restrict__
 }
 
 // cols[c][i] -= sum_j alpha_j[code_j[i]][col0 + c]
-struct ApplyTabs {
-  const int32_t* code[LFE_MAX_FE];
-  const double* alpha[LFE_MAX_FE];
-  int n;
-};
+typedef ProjOthers ApplyTabs;   // code[j] in ROW order here; small tables are staged in shared memory too
 template <int NC>
 __global__ void __launch_bounds__(256) k_apply(MutColPtrs cols, ApplyTabs T, int64_t n, int ldc, int col0) {
+  extern __shared__ double sm_tabs[];
+  const double* tabs[LFE_MAX_FE];
+  stage_tables(T, ldc, sm_tabs, tabs);
   const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double s[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) s[c] = 0.0;
     for (int j = 0; j < T.n; ++j) {
-      const double* row = T.alpha[j] + (size_t)__ldcs(T.code[j] + i) * ldc + col0;
+      const double* row = tabs[j] + (size_t)__ldcs(T.code[j] + i) * ldc + col0;
       if (vec2) {
 #pragma unroll
         for (int c = 0; c < NC / 2; ++c) {
-          double2 t = __ldg(reinterpret_cast<const double2*>(row) + c);
+          double2 t = *(reinterpret_cast<const double2*>(row) + c);
           s[2 * c] += t.x;
           s[2 * c + 1] += t.y;
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) s[c] += __ldg(row + c);
+        for (int c = 0; c < NC; ++c) s[c] += row[c];
       }
     }
 #pragma unroll
@@ -230,16 +264,31 @@ struct FEState {
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// decide which tables are small enough to be staged in shared memory; returns the dynamic smem bytes
+static size_t plan_staging(ProjOthers& o, const int64_t* rows, int ldc) {
+  size_t used = 0;
+  for (int q = 0; q < o.n; ++q) {
+    size_t bytes = (((size_t)rows[q] * ldc + 1) & ~(size_t)1) * sizeof(double);
+    if (rows[q] > 0 && used + bytes <= (size_t)STAGE_SMEM_BYTES) {
+      o.stage_rows[q] = (int)rows[q];
+      used += bytes;
+    } else {
+      o.stage_rows[q] = 0;
+    }
+  }
+  return used;
+}
+
 template <bool WEIGHTED>
 static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers& oth, int64_t n, int ldc, int col0,
-                        double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
-  int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
-  int blocks = launch_blocks(h, nchunk, 8);
+                        double* acc, int ld_acc, int acc_col0, size_t smem, cudaStream_t s) {
+  int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I * PJ_NB);
+  int blocks = launch_blocks(h, nchunk, 2);   // persistent: 2 CTAs per SM (register-limited), tables staged once
   bool vec = aligned16(st.key);
   for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
-#define PJ_CASE(NC_)                                                                                             \
-  case NC_:                                                                                                      \
-    k_proj<NC_, WEIGHTED><<<blocks, PJ_T, 0, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc, acc_col0, vec); \
+#define PJ_CASE(NC_)                                                                                                \
+  case NC_:                                                                                                         \
+    k_proj<NC_, WEIGHTED><<<blocks, PJ_T, smem, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc, acc_col0, vec); \
     break;
   switch (nc) {
     PJ_CASE(1) PJ_CASE(2) PJ_CASE(3) PJ_CASE(4) PJ_CASE(5) PJ_CASE(6) PJ_CASE(7) PJ_CASE(8)
@@ -301,10 +350,10 @@ static void launch_groupsum(lfe_ctx* h, int nc, const int32_t* key, int64_t G, c
 }
 
 static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const ApplyTabs& T, int64_t n, int ldc, int col0,
-                         cudaStream_t s) {
-  int blocks = launch_blocks(h, ceil_div64(n, 256), 8);
+                         size_t smem, cudaStream_t s) {
+  int blocks = launch_blocks(h, ceil_div64(n, 256), smem > 0 ? 4 : 8);
 #define AP_CASE(NC_) \
-  case NC_: k_apply<NC_><<<blocks, 256, 0, s>>>(cols, T, n, ldc, col0); break;
+  case NC_: k_apply<NC_><<<blocks, 256, smem, s>>>(cols, T, n, ldc, col0); break;
   switch (nc) {
     AP_CASE(1) AP_CASE(2) AP_CASE(3) AP_CASE(4) AP_CASE(5) AP_CASE(6) AP_CASE(7) AP_CASE(8)
     default: LFE_THROW(LFE_ERR_ARG, "launch_apply: nc=%d", nc);
@@ -500,16 +549,20 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
     }
   }
 
+  size_t proj_smem = 0;
   auto others_of = [&](int j, bool include_all_for_check) {
     ProjOthers o;
+    int64_t rows[LFE_MAX_FE];
     o.n = 0;
     for (int k = 0; k < F; ++k) {
       if (k == j) continue;
       o.code[o.n] = st[j].oth[k];
       o.alpha[o.n] = st[k].alpha;
+      rows[o.n] = st[k].G;
       o.n++;
     }
     (void)include_all_for_check;
+    proj_smem = plan_staging(o, rows, C);
     return o;
   };
 
@@ -517,33 +570,79 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
   int iterations = 0;
   bool converged = false;
   double max_mean = 0.0;
+
+  // accumulate the projection sums of FE j over all column batches (+ cross-rank sum for non-local FEs)
+  auto project = [&](int j) {
+    FEState& S = st[j];
+    if (F == 1) return;
+    ProjOthers o = others_of(j, false);
+    for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
+      int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+      if (weighted) launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+      else launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+    }
+    if (dist && j != local_fe) {
+      PhaseTimer tc(h, s, 13);
+      comm_allreduce(h, S.acc, S.G * C, 0, s);
+    }
+  };
+  // Unweighted fits: the reference's stopping quantity for the FIRST FE of the sweep order,
+  // max_g |mean_g(y)| after sweep `it`, IS the y-column update that FE receives at the start of sweep it+1.
+  // So the check runs that projection speculatively into a staging table (kept if the loop goes on,
+  // dropped if it stops); the LAST FE of the order was projected last, its group means are exactly zero in
+  // coefficient space; only the middle FEs (F >= 3) need a y-only pass.
+  const bool fast_check = !weighted && !strict_check && F >= 2 && tol > 1e-13;
+  DevBuf<double> alpha_next;
+  if (fast_check) alpha_next.alloc((size_t)st[fe_order[0]].G * C, s);
+  bool first_done = false;   // sweep it+1's first projection was already applied by the check of sweep it
+
   for (int it = 1; it <= max_iter; ++it) {
     if (strict_check) dmax.zero();
     {
       PhaseTimer t(h, s, 6);
-      for (int oi = 0; oi < F; ++oi) {
+      for (int oi = first_done ? 1 : 0; oi < F; ++oi) {
         int j = fe_order[oi];
         FEState& S = st[j];
-        if (F > 1) {
-          ProjOthers o = others_of(j, false);
-          for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
-            int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
-            if (weighted) launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, s);
-            else launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, s);
-          }
-          if (dist && j != local_fe) {
-            PhaseTimer tc(h, s, 13);
-            comm_allreduce(h, S.acc, S.G * C, 0, s);
-          }
-        }
-        k_finalize<<<launch_blocks(h, ceil_div64(S.G * C, 256), 8), 256, 0, s>>>(S.alpha, S.acc, S.S0, S.nsum, S.G, C,
-                                                                                 strict_check ? dmax.p : nullptr);
+        project(j);
+        k_finalize<<<launch_blocks(h, ceil_div64(S.G * C, 256), 8), 256, 0, s>>>(
+            S.alpha, S.alpha, S.acc, S.S0, S.nsum, S.G, C, strict_check ? dmax.p : nullptr, -1);
         KERNEL_CHECK();
         h->n_launches += 1;
       }
+      first_done = false;
     }
     iterations = it;
-    if (it >= min_iter && strict_check) {
+    if (it >= min_iter && fast_check) {
+      PhaseTimer t(h, s, 7);
+      dmax.zero();
+      for (int oi = 1; oi + 1 < F; ++oi) {   // middle FEs: explicit y-only group means
+        FEState& S = st[fe_order[oi]];
+        ProjOthers o = others_of(fe_order[oi], true);
+        launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
+        if (dist && fe_order[oi] != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
+        k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
+                                                                           S.G, C, dmax);
+        KERNEL_CHECK();
+        h->n_launches += 1;
+      }
+      FEState& S1 = st[fe_order[0]];
+      project(fe_order[0]);
+      k_finalize<<<launch_blocks(h, ceil_div64(S1.G * C, 256), 8), 256, 0, s>>>(S1.alpha, alpha_next, S1.acc, S1.S0,
+                                                                                  S1.nsum, S1.G, C, dmax, 0);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      if (dist) comm_allreduce(h, dmax, 1, 1, s);
+      CUDA_CHECK(cudaMemcpyAsync(&max_mean, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (max_mean < tol) {
+        converged = true;
+        break;
+      }
+      if (it < max_iter) {   // keep the speculative projection: it is sweep it+1's first step
+        std::swap(S1.alpha, alpha_next);
+        first_done = true;
+      }
+    } else if (it >= min_iter && strict_check) {
       // true fixed-point test: the largest (weighted) group mean removed during this sweep, all columns
       PhaseTimer t(h, s, 7);
       if (dist) comm_allreduce(h, dmax, 1, 1, s);
@@ -560,7 +659,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
         FEState& S = st[j];
         if (F > 1) {
           ProjOthers o = others_of(j, true);
-          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, s);
+          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
           if (dist && j != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
         }
         k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
@@ -582,16 +681,19 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
   {
     PhaseTimer t(h, s, 8);
     ApplyTabs T;
+    int64_t rows[LFE_MAX_FE];
     T.n = F;
     for (int j = 0; j < F; ++j) {
       T.code[j] = codes[j];
       T.alpha[j] = st[j].alpha;
+      rows[j] = st[j].G;
     }
+    const size_t apply_smem = plan_staging(T, rows, C);
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
       MutColPtrs mp;
       for (int c = 0; c < nc; ++c) mp.col[c] = cols[c0 + c];
-      if (n > 0) launch_apply(h, nc, mp, T, n, C, c0, s);
+      if (n > 0) launch_apply(h, nc, mp, T, n, C, c0, apply_smem, s);
     }
   }
   *iterations_out = iterations;

@@ -9,8 +9,26 @@ constexpr int PJ_MAXNC = 8;
 struct ProjOthers {
   const int32_t* code[LFE_MAX_FE];
   const double* alpha[LFE_MAX_FE];
+  int stage_rows[LFE_MAX_FE];  // > 0: copy that many table rows into shared memory at CTA start (small tables)
   int n;
 };
+constexpr int STAGE_SMEM_BYTES = 48 * 1024;
+
+// Copy the small tables into shared memory; tabs[o] then points at the staged copy (generic address space).
+__device__ __forceinline__ void stage_tables(const ProjOthers& oth, int ldc, double* smem, const double* tabs[LFE_MAX_FE]) {
+  int off = 0;
+  for (int o = 0; o < oth.n; ++o) {
+    if (oth.stage_rows[o] > 0) {
+      const int cnt = oth.stage_rows[o] * ldc;
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[off + i] = __ldg(oth.alpha[o] + i);
+      tabs[o] = smem + off;
+      off += (cnt + 1) & ~1;   // keep 16-byte alignment for the double2 gathers
+    } else {
+      tabs[o] = oth.alpha[o];
+    }
+  }
+  __syncthreads();
+}
 struct ColPtrs {
   const double* col[PJ_MAXNC];
 };
@@ -28,17 +46,13 @@ __device__ __forceinline__ void load4_i32(const int32_t* __restrict__ p, int64_t
   }
 }
 
-// Flush thread-local runs and segmented-reduce the open (tail) runs across the warp.
+// Fold PJ_I consecutive entries into the thread's open run (cur, run): equal keys accumulate, a key change
+// flushes the finished run with RED.ADD.F64.  cur < 0 = no open run / padding entry.
 template <int NC>
-__device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ_I][NC], double* __restrict__ acc,
-                                                int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
-  const int lane = threadIdx.x & 31;
-  int cur = key[0];
-  double run[NC];
+__device__ __forceinline__ void run_fold(int& cur, double run[NC], const int key[PJ_I], double v[PJ_I][NC],
+                                         double* __restrict__ acc, int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
 #pragma unroll
-  for (int c = 0; c < NC; ++c) run[c] = v[0][c];
-#pragma unroll
-  for (int e = 1; e < PJ_I; ++e) {
+  for (int e = 0; e < PJ_I; ++e) {
     if (key[e] == cur) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) run[c] += v[e][c];
@@ -53,6 +67,13 @@ __device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ
       for (int c = 0; c < NC; ++c) run[c] = v[e][c];
     }
   }
+}
+
+// Segmented-reduce the threads' open runs across the warp and flush one total per (warp, key).
+template <int NC>
+__device__ __forceinline__ void warp_flush(int cur, double run[NC], double* __restrict__ acc, int64_t ld_row,
+                                           int acc_col0, int64_t ld_col = 1) {
+  const int lane = threadIdx.x & 31;
   // inclusive segmented scan of the tail runs.  Segments are maximal runs of ADJACENT lanes with equal
   // keys (head flags), so the result is exact for unsorted keys too (equal keys that are not adjacent
   // simply end up in separate atomics).
@@ -74,5 +95,17 @@ __device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ
 #pragma unroll
     for (int c = 0; c < NC; ++c) atomicAdd(a + (size_t)c * ld_col, run[c]);
   }
+}
+
+// one batch of PJ_I entries per thread: fold + warp flush
+template <int NC>
+__device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ_I][NC], double* __restrict__ acc,
+                                                int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
+  int cur = -1;
+  double run[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) run[c] = 0.0;
+  run_fold<NC>(cur, run, key, v, acc, ld_row, acc_col0, ld_col);
+  warp_flush<NC>(cur, run, acc, ld_row, acc_col0, ld_col);
 }
 

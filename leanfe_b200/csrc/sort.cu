@@ -5,13 +5,28 @@
 // width is chosen per sort so that the key bits split evenly over the fewest passes (20-bit unit
 // codes: 2 x 10; 9-bit period codes: 1 x 9).  Each pass is histogram -> exclusive scan -> scatter;
 // ranks inside a tile come from warp-level __match_any_sync in element order, which keeps every pass
-// stable and the whole sort deterministic.
+// stable and the whole sort deterministic.  (Ranks use BITS warp ballots per element, not MATCH.ANY.)
 #include "common.cuh"
 
 constexpr int RS_T = 256;
 constexpr int RS_NW = RS_T / 32;
 constexpr int RS_I = 16;
 constexpr int RS_TILE = RS_T * RS_I;
+
+// Lanes holding the same digit as this lane (the lane itself included), among valid lanes.  BITS ballots:
+// fixed cost, unlike MATCH.ANY whose latency grows with the number of distinct values in the warp -- and
+// with 9/10-bit digits of random codes nearly all 32 values are distinct.
+template <int BITS>
+__device__ __forceinline__ uint32_t warp_peers(uint32_t d, bool valid) {
+  uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < BITS; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
 
 template <typename KeyT, int BITS>
 __global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ keys, int64_t n, int shift,
@@ -26,8 +41,8 @@ __global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ ke
   for (int i = 0; i < RS_I; ++i) {
     int64_t idx = base + (int64_t)i * RS_T + threadIdx.x;
     bool valid = idx < n;
-    uint32_t d = valid ? (uint32_t)((keys[idx] >> shift) & (BINS - 1)) : (uint32_t)(BINS + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t d = valid ? (uint32_t)((__ldcs(keys + idx) >> shift) & (BINS - 1)) : 0u;
+    uint32_t peers = warp_peers<BITS>(d, valid);
     if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&cnt[d], __popc(peers));
   }
   __syncthreads();
@@ -35,7 +50,7 @@ __global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ ke
 }
 
 template <typename KeyT, int BITS>
-__global__ void __launch_bounds__(RS_T) k_radix_scatter(const KeyT* __restrict__ keys_in,
+__global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restrict__ keys_in,
                                                         const uint32_t* __restrict__ vals_in,
                                                         KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                         int64_t n, int shift, const uint32_t* __restrict__ offsets,
@@ -62,13 +77,16 @@ __global__ void __launch_bounds__(RS_T) k_radix_scatter(const KeyT* __restrict__
   for (int r = 0; r < RS_I; ++r) {
     int64_t idx = wbase + r * 32 + lane;
     bool valid = idx < n;
-    uint32_t d = valid ? (uint32_t)((k[r] >> shift) & (BINS - 1)) : (uint32_t)(BINS + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t base = valid ? wcnt[warp][d] : 0u;
-    __syncwarp();
+    uint32_t d = valid ? (uint32_t)((k[r] >> shift) & (BINS - 1)) : 0u;
+    uint32_t peers = warp_peers<BITS>(d, valid);
+    // the group leader bumps the warp's digit counter; the returned old value is the rank base of this round.
+    // Same-warp atomics on one address retire in program order, so rounds need no barrier between them and
+    // rounds that touch different digits overlap freely.
+    const int leader = valid ? (__ffs(peers) - 1) : lane;
+    uint32_t base = 0u;
+    if (valid && lane == leader) base = atomicAdd(&wcnt[warp][d], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
     rk[r] = base + __popc(peers & lt);
-    if (valid && lane == (__ffs(peers) - 1)) wcnt[warp][d] = base + __popc(peers);
-    __syncwarp();
   }
   __syncthreads();
   for (int t = threadIdx.x; t < BINS; t += RS_T) {
