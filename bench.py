@@ -66,19 +66,29 @@ def sample_for_cpu(d: dict, G1: int, target_rows: int):
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  Started BEFORE the warm-up (nvidia-smi needs
+    ~100 ms to come up); only samples whose timestamp falls inside [mark_start(), stop()] are reported."""
+
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.t0 = None
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                        "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
     def stop(self):
+        t1 = time.time()
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -86,23 +96,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]),
+                             [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= t1 + 0.02]
+        if not inside and rows:          # region shorter than the sampling period: take the closest samples
+            mid = 0.5 * ((self.t0 or t1) + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+        reasons = sorted({x for r in inside for x in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None,
+                "samples": len(inside), "reasons": reasons}
 
 
 def cpu_reference_run(d: dict, steps: int, warmup: int):
@@ -188,12 +204,14 @@ def main():
     # ---- device-resident arm ----------------------------------------------------------------------
     resident = {k_: t.to(dev) for k_, t in host.items()}
     res = None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         res = leanfe(resident, **kw)
     eng.set_profiling(True)
     eng.reset_timers()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

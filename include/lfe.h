@@ -99,8 +99,9 @@ int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_gr
  * communicator attached, group sizes of every FE except `local_fe` (-1: none) are summed over the
  * ranks before the test and fe_dims are global.                                                  */
 int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
-                       int64_t n, int local_fe, uint8_t* keep_out, int64_t* n_keep_out /*[host] 2*/,
-                       int64_t* fe_dims_out /*[host] F*/, void* stream);
+                       int64_t n, int local_fe, const int32_t* const* counts /*nullable: rank-local group
+                       sizes from lfe_group_counts, saves one pass per FE*/, uint8_t* keep_out,
+                       int64_t* n_keep_out /*[host] 2*/, int64_t* fe_dims_out /*[host] F*/, void* stream);
 
 /* stable compaction of C double columns and K int32 columns by keep[]; outputs have n_keep rows */
 int lfe_compact(lfe_handle h, const uint8_t* keep, int64_t n,
@@ -142,8 +143,9 @@ int lfe_demean(lfe_handle h, double* const* cols, int C, const int32_t* const* c
  * unchanged until lfe_demean_plan_destroy.  lfe_demean == create + run + destroy.                    */
 typedef struct lfe_plan* lfe_plan_t;
 int lfe_demean_plan_create(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
-                           int64_t n, const double* weights, int local_fe, lfe_plan_t* plan_out,
-                           void* stream);
+                           int64_t n, const double* weights, int local_fe,
+                           const int32_t* const* counts /*nullable, as in lfe_singleton_mask*/,
+                           lfe_plan_t* plan_out, void* stream);
 int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, int C, const int* fe_order,
                         double tol, int max_iter, int min_iter, int flags, int* iterations_out /*[host]*/,
                         double* max_mean_out /*[host]*/, int* converged_out /*[host]*/, void* stream);

@@ -62,13 +62,13 @@ def load_library() -> C.CDLL:
     lib.lfe_get_counters.argtypes = [vp, P(i64)]
     lib.lfe_factorize.argtypes = [vp, vp, i32, i64, i32, vp, P(i64), vp, i64, vp]
     lib.lfe_group_counts.argtypes = [vp, vp, i64, i64, vp, vp]
-    lib.lfe_singleton_mask.argtypes = [vp, P(vp), P(i64), i32, i64, i32, vp, P(i64), P(i64), vp]
+    lib.lfe_singleton_mask.argtypes = [vp, P(vp), P(i64), i32, i64, i32, P(vp), vp, P(i64), P(i64), vp]
     lib.lfe_compact.argtypes = [vp, vp, i64, P(vp), P(vp), i32, P(vp), P(vp), i32, vp]
     lib.lfe_sort_rows.argtypes = [vp, vp, i64, i64, vp, P(i32), vp]
     lib.lfe_gather.argtypes = [vp, vp, i64, P(vp), P(vp), i32, P(vp), P(vp), i32, vp]
     lib.lfe_demean.argtypes = [vp, P(vp), i32, P(vp), P(i64), P(i32), i32, i64, vp, dbl, i32, i32, i32, i32,
                                P(i32), P(dbl), P(i32), vp]
-    lib.lfe_demean_plan_create.argtypes = [vp, P(vp), P(i64), i32, i64, vp, i32, P(vp), vp]
+    lib.lfe_demean_plan_create.argtypes = [vp, P(vp), P(i64), i32, i64, vp, i32, P(vp), P(vp), vp]
     lib.lfe_demean_plan_run.argtypes = [vp, vp, P(vp), i32, P(i32), dbl, i32, i32, i32, P(i32), P(dbl), P(i32), vp]
     lib.lfe_demean_plan_destroy.argtypes = [vp, vp]
     lib.lfe_gram.argtypes = [vp, P(vp), i32, i64, vp, i32, vp, vp]

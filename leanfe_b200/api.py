@@ -132,10 +132,18 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
     base_x = list(x_cols)
 
-    def columns():
+    def xsrc(name, keep_int):
+        # YOCO only groups by the regressors: integer-typed columns (dummies, counts) are factorised as they are,
+        # without a 8-byte-per-row fp64 copy
+        t = up.get(name)
+        if keep_int and isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.uint8, torch.int32, torch.int64):
+            return t
+        return num(name)
+
+    def columns(keep_int=False):
         """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
         y_ = num(y_col)
-        X_ = [num(c) for c in base_x]
+        X_ = [xsrc(c, keep_int) for c in base_x]
         names = list(base_x)
         w_ = num(weights) if weights is not None else None
         # interactions then factors (polars_impl.py:350-365); labels come from the original values
@@ -152,7 +160,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             ref_cat = resolve_reference(kc.labels, ref, var)
             for j, cat in enumerate(kc.labels):
                 if cat != ref_cat:
-                    X_.append((kc.codes == j).to(torch.float64))
+                    X_.append((kc.codes == j).to(torch.uint8 if keep_int else torch.float64))
                     names.append(f"{var}_{cat}")
         return y_, X_, names, w_
 
@@ -212,7 +220,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
                 strategy = determine_strategy(vcov, False, fe_card, MAX_FE_LEVELS, n0, len(get_columns()[2]), est_ratio)
 
     if strategy == "compress":
-        y, X, x_cols, w = get_columns()
+        y, X, x_cols, w = cols_cache[0] if cols_cache else columns(keep_int=True)
         res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
         res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
     else:
@@ -248,7 +256,8 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         Gs = [f.n_groups for f in fe_keys]
         order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
         # singleton filter: one pass, all FEs (polars_impl.py:478-482)
-        keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe)
+        counts = [eng.group_counts(c, g) for c, g in zip(codes, Gs)]       # shared by the filter and the plan
+        keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe, counts)
         n_obs = eng.last_n_keep_global
         if n_keep < codes[0].numel():
             y, X, x_cols, w = get_columns()
@@ -262,11 +271,11 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
             plan = eng.demean_plan(codes, Gs, w, local_fe)
         else:
             # rows are never permuted: the plan sorts only the int32 code columns (one entry list per FE)
-            plan = eng.demean_plan(codes, Gs, w, local_fe)
+            plan = eng.demean_plan(codes, Gs, w, local_fe, counts)
             y, X, x_cols, w = get_columns()
             k = len(X)
             cols = [c.clone() for c in [y] + X]       # lfe_demean works in place; never touch caller data
-        del keep
+        del keep, counts
         if strategy == "demean":
             plan.run(cols, order, tol, 1, 2)
             iterations, converged = 1, True
@@ -312,7 +321,7 @@ def _fit_compress(eng: Engine, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_
     xk = []
     for c in X:
         codes, G, uniq = eng.factorize(c, want_uniques=True, uniques_cap=1 << 20)
-        xk.append((codes, G, uniq))
+        xk.append((codes, G, uniq.to(torch.float64)))
     kc = [(c, G) for c, G, _ in xk] + [(f.codes, f.n_groups) for f in fe_keys]
     cl_idx = []
     for name, ck in zip(cluster_cols or [], cl_keys):

@@ -7,7 +7,8 @@
 int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
                            void* uniques, int64_t uniques_cap, cudaStream_t s);
 void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                         int local_fe, uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s);
+                         int local_fe, const int32_t* const* counts_in, uint8_t* keep, int64_t* n_keep_out,
+                         int64_t* fe_dims_out, cudaStream_t s);
 void compact_impl(lfe_ctx* h, const uint8_t* keep, int64_t n, const double* const* f64_in, double* const* f64_out,
                   int C, const int32_t* const* i32_in, int32_t* const* i32_out, int K, cudaStream_t s);
 void sort_rows_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t n_groups, int32_t* perm_out,
@@ -19,7 +20,7 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
                  int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
                  cudaStream_t s);
 lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                             const double* weights, int local_fe, cudaStream_t s);
+                             const double* weights, int local_fe, const int32_t* const* counts_in, cudaStream_t s);
 void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, const int* fe_order, double tol,
                      int max_iter, int min_iter, int flags, int* iterations_out, double* max_mean_out,
                      int* converged_out, cudaStream_t s);
@@ -239,11 +240,12 @@ int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_gr
 }
 
 int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                       int local_fe, uint8_t* keep_out, int64_t* n_keep_out, int64_t* fe_dims_out, void* stream) {
+                       int local_fe, const int32_t* const* counts, uint8_t* keep_out, int64_t* n_keep_out,
+                       int64_t* fe_dims_out, void* stream) {
   LFE_API_BEGIN
   LFE_REQUIRE(h && codes && n_groups && keep_out && n_keep_out, "lfe_singleton_mask: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
-  singleton_mask_impl(h, codes, n_groups, F, n, local_fe, keep_out, n_keep_out, fe_dims_out, S(stream));
+  singleton_mask_impl(h, codes, n_groups, F, n, local_fe, counts, keep_out, n_keep_out, fe_dims_out, S(stream));
   LFE_API_END
 }
 
@@ -284,11 +286,12 @@ int lfe_demean(lfe_handle h, double* const* cols, int C, const int32_t* const* c
 }
 
 int lfe_demean_plan_create(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                           const double* weights, int local_fe, lfe_plan_t* plan_out, void* stream) {
+                           const double* weights, int local_fe, const int32_t* const* counts, lfe_plan_t* plan_out,
+                           void* stream) {
   LFE_API_BEGIN
   LFE_REQUIRE(h && codes && n_groups && plan_out, "lfe_demean_plan_create: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
-  *plan_out = demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, S(stream));
+  *plan_out = demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, counts, S(stream));
   LFE_API_END
 }
 int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, int C, const int* fe_order, double tol,

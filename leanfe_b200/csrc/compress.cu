@@ -2,23 +2,31 @@
 // Reference: python/leanfe/compress.py:325-350 (group_by(x + fe + cluster).agg(len, sum y, sum y^2)) and
 // the distinct count of estimate_compression_ratio (compress.py:249-250).
 //
-// The K code columns are folded into one mixed-radix uint64 key (most significant = first column, so
-// ascending key order == ascending lexicographic order of the code tuples), the key is factorised with
-// the same direct-table / radix-sort machinery as the FE ids, and counts / sum w / sum w y / sum w y^2
-// are by-key reductions.  Keys and counts are exact integers, hence bit-reproducible; the floating
-// sums differ from a sequential group-by only by summation order.
+// The K code columns are folded into a mixed-radix key (most significant = first column, so ascending key
+// order == ascending lexicographic order of the code tuples) and the key is factorised.  Folding is STAGED:
+// columns are accumulated while the product of their cardinalities stays below 2^26, then that partial key
+// is replaced by its dense sorted rank (direct-address table, three streaming passes) before more columns
+// are folded in.  Ranks are order-preserving, so the final group order is still lexicographic, and the
+// composite key of, e.g., 23 dummies x 1000 groups x 24 periods (2e11 combinations, 24 000 present) never
+// needs a 38-bit radix sort.  Counts / sum w / sum w y / sum w y^2 are by-key reductions.  Keys and counts
+// are exact integers, hence bit-reproducible; the floating sums differ from a sequential group-by only by
+// summation order.
+#include <vector>
+
 #include "common.cuh"
 #include "segreduce.cuh"
 
 int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t n, int order, int32_t* codes,
                            void* uniques, int64_t uniques_cap, cudaStream_t s);
 
+constexpr int CP_MAXK = 32;
+constexpr unsigned long long CP_STAGE_SPACE = 1ull << 26;
+
 struct KeyCols {
-  const int32_t* code[32];
-  unsigned long long radix[32];
+  const int32_t* code[CP_MAXK + 1];
+  unsigned long long radix[CP_MAXK + 1];
   int K;
 };
-constexpr int CP_MAXK = 32;
 
 __global__ void __launch_bounds__(256) k_fold_keys(KeyCols kc, int64_t n, uint64_t* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -28,16 +36,19 @@ __global__ void __launch_bounds__(256) k_fold_keys(KeyCols kc, int64_t n, uint64
   }
 }
 
+// One decode step on the G final groups: key = uniq[code_in[g]] -> digits.  Digit 0 may be the code of the
+// previous stage (written to prev_code_out), the others are original columns (written to their outputs).
 struct KeyOut {
-  int32_t* code[32];
-  unsigned long long radix[32];
+  int32_t* code[CP_MAXK + 1];   // nullptr = discard
+  unsigned long long radix[CP_MAXK + 1];
   int K;
 };
-__global__ void __launch_bounds__(256) k_unfold_keys(const uint64_t* __restrict__ uniq, int64_t G, KeyOut ko) {
+__global__ void __launch_bounds__(256) k_unfold_keys(const uint64_t* __restrict__ uniq,
+                                                     const int32_t* __restrict__ code_in, int64_t G, KeyOut ko) {
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x) {
-    unsigned long long key = uniq[g];
+    unsigned long long key = uniq[code_in ? code_in[g] : g];
     for (int j = ko.K - 1; j >= 0; --j) {
-      ko.code[j][g] = (int32_t)(key % ko.radix[j]);
+      if (ko.code[j]) ko.code[j][g] = (int32_t)(key % ko.radix[j]);
       key /= ko.radix[j];
     }
   }
@@ -68,6 +79,14 @@ __global__ void __launch_bounds__(PJ_T) k_group_stats(const int32_t* __restrict_
 
 void prim_histogram(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, uint32_t* counts, cudaStream_t s);
 
+struct Stage {
+  std::vector<int> cols;                 // original column indices folded in this stage (after the previous stage's code)
+  bool has_prev = false;                 // digit 0 = code of the previous stage
+  unsigned long long prev_radix = 1;
+  DevBuf<uint64_t> uniq;                 // sorted distinct folded keys of this stage
+  int64_t G = 0;
+};
+
 void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n_groups, int K, const double* y,
                    const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
                    int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
@@ -79,38 +98,81 @@ void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n
     *n_compressed_out = 0;
     return;
   }
-  KeyCols kc;
-  kc.K = K;
-  long double space = 1.0L;
-  for (int j = 0; j < K; ++j) {
-    LFE_REQUIRE(n_groups[j] >= 1, "lfe_compress: n_groups[%d] must be >= 1", j);
-    kc.code[j] = key_codes[j];
-    kc.radix[j] = (unsigned long long)n_groups[j];
-    space *= (long double)n_groups[j];
-  }
-  LFE_REQUIRE(space < 1.8e19L, "lfe_compress: composite key space overflows 64 bits; pre-combine key columns");
-  DevBuf<uint64_t> folded(n, s), uniq(n, s);
-  DevBuf<int32_t> gcode(n, s);
-  int blocks = launch_blocks(h, ceil_div64(n, 1024), 8);
-  k_fold_keys<<<blocks, 256, 0, s>>>(kc, n, folded);
-  KERNEL_CHECK();
-  h->n_launches += 1;
-  int64_t G = factorize_dispatch(h, folded, LFE_U64, n, LFE_ORDER_SORTED, gcode, uniq, n, s);
+  for (int j = 0; j < K; ++j) LFE_REQUIRE(n_groups[j] >= 1, "lfe_compress: n_groups[%d] must be >= 1", j);
+  const int blocks = launch_blocks(h, ceil_div64(n, 1024), 8);
+  const bool want_keys = key_codes_out != nullptr;
+
+  // ---- staged folding -------------------------------------------------------------------------------
+  std::vector<Stage> stages;
+  DevBuf<uint64_t> folded(n, s);
+  DevBuf<int32_t> gcode(n, s), gcode_prev;
+  int64_t G = 1;
+  int j = 0;
+  bool first = true;
+  do {
+    stages.emplace_back();
+    Stage& st = stages.back();
+    KeyCols kc;
+    kc.K = 0;
+    unsigned long long space = 1;
+    if (!first) {   // carry the previous stage's dense code as the most significant digit
+      st.has_prev = true;
+      st.prev_radix = (unsigned long long)G;
+      std::swap(gcode, gcode_prev);
+      if (!gcode.p) gcode.alloc(n, s);
+      kc.code[kc.K] = gcode_prev;
+      kc.radix[kc.K++] = (unsigned long long)G;
+      space = (unsigned long long)G;
+    }
+    while (j < K) {
+      unsigned long long r = (unsigned long long)n_groups[j];
+      bool fits = space <= CP_STAGE_SPACE / r || (kc.K == (st.has_prev ? 1 : 0));   // always take at least one column
+      if (!fits) break;
+      LFE_REQUIRE(space <= (~0ull) / r, "lfe_compress: composite key space overflows 64 bits");
+      kc.code[kc.K] = key_codes[j];
+      kc.radix[kc.K++] = r;
+      space *= r;
+      st.cols.push_back(j++);
+    }
+    k_fold_keys<<<blocks, 256, 0, s>>>(kc, n, folded);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    // distinct keys of this stage never exceed n; cap the uniques buffer by the key space
+    int64_t ucap = (int64_t)((space < (unsigned long long)n) ? space : (unsigned long long)n);
+    if (want_keys) st.uniq.alloc((size_t)ucap, s);   // only the decode step below needs the stage's distinct keys
+    G = factorize_dispatch(h, folded, LFE_U64, n, LFE_ORDER_SORTED, gcode, st.uniq.p, ucap, s);
+    st.G = G;
+    first = false;
+  } while (j < K);
+
   *n_compressed_out = G;
   if (G > out_cap) {
     if (key_codes_out || cnt_out || n_out) LFE_THROW(LFE_ERR_CAPACITY, "lfe_compress: %lld groups exceed out_cap %lld", (long long)G, (long long)out_cap);
     return;
   }
-  if (key_codes_out) {
-    KeyOut ko;
-    ko.K = K;
-    for (int j = 0; j < K; ++j) {
-      ko.code[j] = key_codes_out[j];
-      ko.radix[j] = kc.radix[j];
+  // ---- decode the final groups back to per-column codes, last stage first --------------------------------
+  if (want_keys) {
+    DevBuf<int32_t> ca(G, s), cb(G, s);
+    const int32_t* code_in = nullptr;   // nullptr: identity (final groups are the last stage's ranks)
+    int32_t* code_out = ca;
+    for (int si = (int)stages.size() - 1; si >= 0; --si) {
+      Stage& st = stages[si];
+      KeyOut ko;
+      ko.K = 0;
+      if (st.has_prev) {
+        ko.code[ko.K] = code_out;
+        ko.radix[ko.K++] = st.prev_radix;
+      }
+      for (int c : st.cols) {
+        ko.code[ko.K] = key_codes_out[c];
+        ko.radix[ko.K++] = (unsigned long long)n_groups[c];
+      }
+      k_unfold_keys<<<launch_blocks(h, ceil_div64(G, 256), 8), 256, 0, s>>>(st.uniq, code_in, G, ko);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      code_in = code_out;
+      code_out = (code_out == ca.p) ? cb.p : ca.p;
     }
-    k_unfold_keys<<<launch_blocks(h, ceil_div64(G, 256), 8), 256, 0, s>>>(uniq, G, ko);
-    KERNEL_CHECK();
-    h->n_launches += 1;
   }
   if (cnt_out) prim_histogram(h, gcode, n, G, (uint32_t*)cnt_out, s);
   if (y && n_out && sum_y_out && sum_y_sq_out) {

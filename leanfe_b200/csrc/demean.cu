@@ -377,7 +377,7 @@ struct lfe_plan {
 };
 
 lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                             const double* weights, int local_fe, cudaStream_t s) {
+                             const double* weights, int local_fe, const int32_t* const* counts_in, cudaStream_t s) {
   LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_demean: F=%d out of range [1,%d]", F, LFE_MAX_FE);
   LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_demean: n out of range");
   const bool weighted = weights != nullptr;
@@ -456,11 +456,16 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
       FEState& S = st[j];
       S.nsum.alloc(S.G, s);
       {
-        DevBuf<uint32_t> c32(S.G, s);
-        prim_histogram(h, codes[j], n, S.G, c32, s);
+        DevBuf<uint32_t> c32;
+        const uint32_t* cnt32 = (counts_in && counts_in[j]) ? (const uint32_t*)counts_in[j] : nullptr;
+        if (!cnt32) {
+          c32.alloc(S.G, s);
+          prim_histogram(h, codes[j], n, S.G, c32, s);
+          cnt32 = c32;
+        }
         DevBuf<double>& dst = weighted ? S.cnt_buf : S.nsum;
         if (weighted) S.cnt_buf.alloc(S.G, s);
-        prim_u32_to_f64(h, c32, S.G, dst, s);
+        prim_u32_to_f64(h, cnt32, S.G, dst, s);
       }
       if (weighted) {
         S.nsum.zero();
@@ -705,7 +710,7 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
                  const int* fe_order, int F, int64_t n, const double* weights, double tol, int max_iter, int min_iter,
                  int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
                  cudaStream_t s) {
-  std::unique_ptr<lfe_plan> plan(demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, s));
+  std::unique_ptr<lfe_plan> plan(demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, nullptr, s));
   demean_plan_run(h, plan.get(), cols, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
                   converged_out, s);
 }

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(256) k_count_nonzero(const uint32_t* __restric
 // Multi-GPU: group sizes of every FE except `local_fe` are summed over the ranks before the test; n_keep_out[0]
 // is the local, n_keep_out[1] the global number of kept rows; fe_dims are global.
 void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
-                         int local_fe, uint8_t* keep, int64_t* n_keep_out, int64_t* fe_dims_out, cudaStream_t s) {
+                         int local_fe, const int32_t* const* counts_in, uint8_t* keep, int64_t* n_keep_out,
+                         int64_t* fe_dims_out, cudaStream_t s) {
   PhaseTimer t(h, s, 1);
   LFE_REQUIRE(F >= 1 && F <= LFE_MAX_FE, "lfe_singleton_mask: F=%d out of range", F);
   const bool dist = h->world > 1;
@@ -398,7 +399,11 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
   CodePtrs P;
   for (int j = 0; j < F; ++j) {
     cnts[j].alloc((size_t)n_groups[j], s);
-    prim_histogram(h, codes[j], n, n_groups[j], cnts[j], s);
+    if (counts_in && counts_in[j])   // rank-local group sizes supplied by the caller (lfe_group_counts)
+      CUDA_CHECK(cudaMemcpyAsync(cnts[j].p, counts_in[j], (size_t)n_groups[j] * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToDevice, s));
+    else
+      prim_histogram(h, codes[j], n, n_groups[j], cnts[j], s);
     if (dist && j != local_fe) comm_allreduce_int(h, cnts[j].p, n_groups[j], 0, 0, s);
     P.code[j] = codes[j];
     P.cnt[j] = cnts[j];

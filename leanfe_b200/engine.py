@@ -123,7 +123,7 @@ class Engine:
         capi.check(self.lib.lfe_group_counts(self.h, self._p(codes), codes.numel(), n_groups, self._p(out), self.stream))
         return out
 
-    def singleton_mask(self, codes: list[torch.Tensor], n_groups: list[int], local_fe: int = -1):
+    def singleton_mask(self, codes: list[torch.Tensor], n_groups: list[int], local_fe: int = -1, counts=None):
         """-> (keep uint8, n_keep on this rank, fe_dims).  ``self.last_n_keep_global`` = kept rows over all ranks."""
         self._check_dev(*codes)
         n = codes[0].numel()
@@ -131,8 +131,9 @@ class Engine:
         n_keep = (C.c_int64 * 2)()
         dims = (C.c_int64 * len(codes))()
         capi.check(self.lib.lfe_singleton_mask(self.h, capi.ptr_array([c.data_ptr() for c in codes]),
-                                               capi.i64_array(n_groups), len(codes), n, int(local_fe), self._p(keep),
-                                               n_keep, dims, self.stream))
+                                               capi.i64_array(n_groups), len(codes), n, int(local_fe),
+                                               capi.ptr_array([c.data_ptr() for c in counts]) if counts else None,
+                                               self._p(keep), n_keep, dims, self.stream))
         self.last_n_keep_global = int(n_keep[1])
         return keep, int(n_keep[0]), tuple(int(d) for d in dims)
 
@@ -190,9 +191,10 @@ class Engine:
         return int(it.value), float(mm.value), bool(cv.value)
 
     def demean_plan(self, codes: list[torch.Tensor], n_groups: list[int], weights: torch.Tensor | None = None,
-                    local_fe: int = -1) -> "DemeanPlan":
-        """Column-independent part of lfe_demean (entry lists, group sizes); see ``DemeanPlan.run``."""
-        return DemeanPlan(self, codes, n_groups, weights, local_fe)
+                    local_fe: int = -1, counts=None) -> "DemeanPlan":
+        """Column-independent part of lfe_demean (entry lists, group sizes); see ``DemeanPlan.run``.
+        ``counts`` (optional) = per-FE int32 group sizes from ``group_counts`` (saves one pass per FE)."""
+        return DemeanPlan(self, codes, n_groups, weights, local_fe, counts)
 
     # -- (4) gram / solve ---------------------------------------------------------------------
     def gram(self, cols: list[torch.Tensor], weights: torch.Tensor | None = None, add_intercept: bool = True):
@@ -320,7 +322,7 @@ class Engine:
 class DemeanPlan:
     """lfe_demean_plan_*: built from the code columns only, runnable on any number of column sets."""
 
-    def __init__(self, eng: Engine, codes, n_groups, weights, local_fe):
+    def __init__(self, eng: Engine, codes, n_groups, weights, local_fe, counts=None):
         eng._check_dev(*codes, weights)
         self.eng, self.codes, self.weights, self.n_groups = eng, list(codes), weights, list(n_groups)   # keep alive
         self.n = codes[0].numel()
@@ -330,7 +332,9 @@ class DemeanPlan:
         p = C.c_void_p()
         capi.check(eng.lib.lfe_demean_plan_create(eng.h, capi.ptr_array([t.data_ptr() for t in codes]),
                                                   capi.i64_array(n_groups), len(codes), self.n, eng._p(weights),
-                                                  int(local_fe), C.byref(p), eng.stream))
+                                                  int(local_fe),
+                                                  capi.ptr_array([c.data_ptr() for c in counts]) if counts else None,
+                                                  C.byref(p), eng.stream))
         self.p = p
 
     def run(self, cols: list[torch.Tensor], fe_order: list[int], tol: float = 1e-6, max_iter: int = 50,
