@@ -259,6 +259,9 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         counts = [eng.group_counts(c, g) for c, g in zip(codes, Gs)]       # shared by the filter and the plan
         keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe, counts)
         n_obs = eng.last_n_keep_global
+        if n_obs == 0:
+            raise ValueError("no observations left after dropping singleton groups (every row is alone in one of "
+                             f"the fixed effects {fe_cols})")
         if n_keep < codes[0].numel():
             y, X, x_cols, w = get_columns()
             k = len(X)

@@ -243,3 +243,33 @@ def test_result_dict_contract():
     assert "x" in r["coefficients"] and r["n_obs"] > 0              # test_basic.py:22-25 spelling
     assert r["vcov_type"] == "iid" and "leanfe Regression Results" in str(r)
     assert r.timings["demean_sweeps"] > 0 and r.timings["launches"] > 0
+
+
+def test_degenerate_inputs_raise_cleanly():
+    from leanfe_b200 import leanfe
+    rng = np.random.default_rng(9)
+    n = 1000
+    d = dict(y=rng.normal(size=n), x=rng.normal(size=n), u=np.arange(n), t=rng.integers(0, 5, n))
+    with pytest.raises(ValueError, match="singleton"):
+        leanfe(d, formula="y ~ x | u + t")                  # every unit is a singleton: nothing left to fit
+    with pytest.raises(KeyError):
+        leanfe(d, formula="y ~ nope | t")
+    with pytest.raises(NotImplementedError):
+        leanfe(d, formula="y ~ x | t | z")                  # IV is out of scope, says so
+
+
+def test_wide_design_twenty_regressors():
+    """Shape of the reference's 20-regressor benchmark (python/tests/benchmark_results2.csv:29), small N."""
+    from leanfe_b200 import leanfe
+    rng = np.random.default_rng(10)
+    n, k = 60_000, 20
+    d = dict(f1=rng.integers(0, 800, n), f2=rng.integers(0, 150, n), f3=rng.integers(0, 40, n))
+    y = rng.normal(size=n)
+    for j in range(k):
+        d[f"x{j}"] = rng.normal(size=n) + 0.02 * d["f1"] / 800
+        y = y + (0.5 + 0.05 * j) * d[f"x{j}"]
+    d["y"] = y
+    f = "y ~ " + " + ".join(f"x{j}" for j in range(k)) + " | f1 + f2 + f3"
+    for vc, cl in (("iid", None), ("hc1", None), ("cluster", ["f2"])):
+        res = leanfe(d, formula=f, vcov=vc, cluster_cols=cl)
+        _check(res, O.leanfe_oracle(d, formula=f, vcov=vc, cluster_cols=cl))

@@ -339,3 +339,62 @@ def test_compress_known_answer_from_reference_docstring(eng):
     np.testing.assert_array_equal(got["cnt"].cpu().numpy(), [2, 1])
     np.testing.assert_allclose(got["sum_y"].cpu().numpy(), [3.0, 3.0])
     np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), [5.0, 9.0])
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: tiny / ragged inputs, plan reuse, many columns, every row its own group
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 257, 1025])
+def test_tiny_inputs_every_kernel(eng, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, max(n // 3, 1), n).astype(np.int32)
+    b = rng.integers(0, 3, n).astype(np.int32)
+    cols = [rng.normal(size=n) for _ in range(3)]
+    Ga, Gb = int(a.max()) + 1, 3
+    exp_cols, _, _ = O.alt_proj(cols, [a, b], [1, 0] if Gb <= Ga else [0, 1], 0.0, 4)
+    d_cols = [dev(c) for c in cols]
+    eng.demean(d_cols, [dev(a), dev(b)], [Ga, Gb], [1, 0] if Gb <= Ga else [0, 1], None, 0.0, 4, 3)
+    for got, exp in zip(d_cols, exp_cols):
+        np.testing.assert_allclose(got.cpu().numpy(), np.nan_to_num(exp), rtol=0, atol=1e-12)
+    codes, G, uniq = eng.factorize(dev(a.astype(np.int64) * 5 - 2), want_uniques=True)
+    np.testing.assert_array_equal(codes.cpu().numpy(), O.codes_sorted(a)[0])
+    perm, _ = eng.sort_rows(dev(a), Ga)
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(a, kind="stable"))
+    got = eng.gram([dev(c) for c in cols], None, True).cpu().numpy()
+    Z = np.column_stack([np.ones(n)] + cols)
+    np.testing.assert_allclose(got, Z.T @ Z, rtol=1e-12, atol=1e-12)
+    comp = eng.compress([dev(a), dev(b)], [Ga, Gb], dev(cols[0]))
+    exp = O.compress(cols[0], [a, b])
+    assert comp["n_compressed"] == exp["n_compressed"]
+    np.testing.assert_array_equal(comp["cnt"].cpu().numpy(), exp["n"].astype(np.int64))
+
+
+def test_demean_plan_reuse_and_many_columns(eng):
+    rng = np.random.default_rng(77)
+    n, Gs = 80_000, (4000, 25)
+    codes = [rng.integers(0, g, n).astype(np.int32) for g in Gs]
+    w = rng.uniform(0.5, 2.0, n)
+    plan = eng.demean_plan([dev(c) for c in codes], list(Gs), dev(w))
+    for C in (1, 9, 20):                                   # 20 columns = three column batches
+        cols = [rng.normal(size=n) + 0.01 * codes[0] for _ in range(C)]
+        exp_cols, exp_it, _ = O.alt_proj(cols, codes, [1, 0], 0.0, 5, w)
+        d_cols = [dev(c) for c in cols]
+        it, _, _ = plan.run(d_cols, [1, 0], 0.0, 5, 3)
+        assert it == exp_it
+        for got, exp in zip(d_cols, exp_cols):
+            np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=1e-11)
+    plan.close()
+
+
+def test_every_row_its_own_group_and_one_group(eng):
+    rng = np.random.default_rng(5)
+    n = 40_000
+    a = rng.permutation(n).astype(np.int32)                # G == n
+    b = np.zeros(n, dtype=np.int32)                        # G == 1
+    cols = [rng.normal(size=n) for _ in range(2)]
+    d_cols = [dev(c) for c in cols]
+    it, _, conv = eng.demean(d_cols, [dev(a), dev(b)], [n, 1], [1, 0], None, 1e-6, 50, 3)
+    for got in d_cols:                                      # each row is its own group: everything is absorbed
+        assert float(got.abs().max()) < 1e-12
+    keep, n_keep, dims = eng.singleton_mask([dev(a), dev(b)], [n, 1])
+    assert n_keep == 0 and dims == (0, 0) and int(keep.sum()) == 0
