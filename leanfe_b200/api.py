@@ -117,9 +117,14 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     numeric: dict[str, torch.Tensor] = {}
     keys: dict[str, KeyColumn] = {}
 
+    owned_ids: set[int] = set()      # device tensors created by this call (uploads, casts): safe to overwrite
+
     def num(name):
         if name not in numeric:
-            numeric[name] = to_device_f64(eng, up.get(name))
+            src = up.get(name)
+            numeric[name] = to_device_f64(eng, src)
+            if name in up.events_seen or numeric[name] is not src:
+                owned_ids.add(id(numeric[name]))
         return numeric[name]
 
     def key(name, labels=False):
@@ -169,7 +174,14 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     def get_columns():
         if not cols_cache:
             cols_cache.append(columns())
+            owned_ids.update(id(t) for t in cols_cache[0][1][len(base_x):])      # expanded dummies are ours
         return cols_cache[0]
+
+    get_columns.owned = lambda t: id(t) in owned_ids
+    if not interactions and not factor_vars and weights is None:
+        # plain columns: they can be handed out one by one, as each upload completes
+        get_columns.lazy = dict(y=y_col, x=base_x, get=num,
+                                pending=lambda: any(nm in up.events for nm in [y_col] + base_x))
 
     n0 = fe_keys[0].codes.numel() if fe_keys else get_columns()[0].numel()
 
@@ -275,17 +287,42 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         else:
             # rows are never permuted: the plan sorts only the int32 code columns (one entry list per FE)
             plan = eng.demean_plan(codes, Gs, w, local_fe, counts)
-            y, X, x_cols, w = get_columns()
-            k = len(X)
-            cols = [c.clone() for c in [y] + X]       # lfe_demean works in place; never touch caller data
+            cols = None
         del keep, counts
-        if strategy == "demean":
-            plan.run(cols, order, tol, 1, 2)
-            iterations, converged = 1, True
-            absorbed = fe_dims[0] - 1
-        else:
-            iterations, _, converged = plan.run(cols, order, tol, max_iter, 3)
+        lazy = getattr(get_columns, "lazy", None)
+        if cols is None and lazy is not None and strategy == "alt_proj" and lazy["pending"]():
+            # Columns are still crossing PCIe.  Demeaning is independent per column and the stopping rule looks
+            # at y only (polars_impl.py:511-525), so: demean y as soon as it lands (this fixes the sweep count
+            # T), then give every regressor exactly T sweeps as it arrives -- the same iterates as the
+            # all-columns loop, but only the last column's work is left when the upload ends.
+            own = get_columns.owned
+
+            def fetch(name):
+                t = lazy["get"](name)
+                return t if own(t) else t.clone()                             # never overwrite caller-owned data
+
+            ycol = fetch(lazy["y"])
+            iterations, _, converged = plan.run([ycol], order, tol, max_iter, 3)
+            cols, x_cols = [ycol], list(lazy["x"])
+            for name in x_cols:
+                c = fetch(name)
+                plan.run([c], order, tol, iterations, iterations + 1)         # T sweeps, no stopping test
+                cols.append(c)
+            k = len(x_cols)
             absorbed = sum(fe_dims) - F
+        else:
+            if cols is None:
+                y, X, x_cols, w = get_columns()
+                k = len(X)
+                own = getattr(get_columns, "owned", lambda t: False)
+                cols = [c if own(c) else c.clone() for c in [y] + X]   # in place, but never on caller-owned data
+            if strategy == "demean":
+                plan.run(cols, order, tol, 1, 2)
+                iterations, converged = 1, True
+                absorbed = fe_dims[0] - 1
+            else:
+                iterations, _, converged = plan.run(cols, order, tol, max_iter, 3)
+                absorbed = sum(fe_dims) - F
         plan.close()
     else:
         y, X, x_cols, w = get_columns()

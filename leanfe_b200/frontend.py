@@ -86,6 +86,7 @@ class Uploader:
         self.dev: dict[str, torch.Tensor] = {}
         self.events: dict[str, torch.cuda.Event] = {}
         self._host_refs: list = []
+        self.events_seen: set[str] = set()     # columns whose device copy was made here (never caller-owned)
         pending = []
         for name in dict.fromkeys(names):
             col = frame.column(name)
@@ -122,6 +123,7 @@ class Uploader:
                     ev.record(self.copy)
                     d.record_stream(self.copy)
                     self.dev[name], self.events[name] = d, ev
+                    self.events_seen.add(name)
                     self._host_refs.append(t)              # keep the source alive until the async copy ran
 
     def get(self, name: str):
