@@ -268,6 +268,119 @@ static void cluster_sandwich(lfe_ctx* h, const int32_t* const* cl_codes, const i
   h->n_launches += 1;
 }
 
+// ---- one-way clustering in ONE pass over the columns --------------------------------------------------
+// r = y - b0 - x'beta, the rss / tss moments, the cluster presence flags and the scores S_g += w x r are all
+// produced while each row is in registers: the regressors are read once instead of twice and the residual
+// vector is never materialised.
+template <int NC>
+__global__ void __launch_bounds__(PJ_T) k_resid_scores(const double* __restrict__ y, ColPtrs X,
+                                                       const double* __restrict__ beta_full,
+                                                       const double* __restrict__ w, const int32_t* __restrict__ key,
+                                                       int64_t n, double* __restrict__ S, uint32_t* __restrict__ present,
+                                                       double* __restrict__ partials, int use_shift, bool vec_codes) {
+  __shared__ double sb[NC + 1];
+  if (threadIdx.x <= NC) sb[threadIdx.x] = beta_full[threadIdx.x];
+  __syncthreads();
+  const double c0 = use_shift ? y[0] : 0.0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    int kk[PJ_I];
+    load4_i32(key, base, n, vec_codes, kk);
+    double v[PJ_I][NC];
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e) {
+      const bool valid = base + e < n;
+      const double yi = valid ? __ldcs(y + base + e) : 0.0;
+      double r = yi - sb[0];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        v[e][c] = valid ? __ldcs(X.col[c] + base + e) : 0.0;
+        r = fma(-sb[c + 1], v[e][c], r);
+      }
+      if (!valid) r = 0.0;
+      const double we = (w && valid) ? __ldcs(w + base + e) : 1.0;
+      const double r2 = r * r;
+      a0 += r2;
+      a1 += we * r2;
+      const double d = valid ? yi - c0 : 0.0;
+      a2 += d;
+      a3 = fma(d, d, a3);
+      const double rw = r * we;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[e][c] *= rw;
+      if (valid) present[kk[e]] = 1u;
+    }
+    segmented_flush<NC>(kk, v, S, NC, 0, 1);
+  }
+  __shared__ double sh[PJ_T / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if (lane == 0) { sh[warp][0] = a0; sh[warp][1] = a1; sh[warp][2] = a2; sh[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int q = 0; q < PJ_T / 32; ++q) t += sh[q][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+  }
+}
+
+static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, int64_t n, const double* beta_full,
+                                 const double* Binv, const int32_t* cl, int64_t Gcap, const double* weights, int ssc,
+                                 int64_t n_obs, int64_t df_resid, bool cl_local, double* se_out, double* vcov_out,
+                                 double* stats_out, int64_t* n_clusters_out, cudaStream_t s) {
+  ColPtrs X;
+  for (int j = 0; j < k; ++j) X.col[j] = cols[1 + j];
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  const int blocks = launch_blocks(h, nchunk, 8);
+  DevBuf<double> S((size_t)Gcap * k, s), partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
+  DevBuf<uint32_t> present(Gcap, s);
+  DevBuf<unsigned long long> tot(1, s);
+  S.zero(); present.zero(); tot.zero();
+  const bool vec = (((uintptr_t)cl) & 15) == 0;
+  const int shift = h->world == 1 ? 1 : 0;
+#define RS_CASE(NC_)                                                                                              \
+  case NC_:                                                                                                       \
+    k_resid_scores<NC_><<<blocks, PJ_T, 0, s>>>(cols[0], X, beta_full, weights, cl, n, S, present, partials, shift, vec); \
+    break;
+  switch (k) { RS_CASE(1) RS_CASE(2) RS_CASE(3) RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8) }
+#undef RS_CASE
+  KERNEL_CHECK();
+  k_resid_final<<<1, 32, 0, s>>>(partials, blocks, (double)n, raw);
+  KERNEL_CHECK();
+  if (h->world > 1) comm_allreduce(h, raw, 4, 0, s);
+  double* stats = stats_out ? stats_out : stats_local.p;
+  k_stats_from_raw<<<1, 32, 0, s>>>(raw, (double)n_obs, stats);
+  KERNEL_CHECK();
+  // number of clusters with at least one row
+  if (h->world > 1 && !cl_local) comm_allreduce_int(h, present.p, Gcap, 0, 2, s);
+  k_sum_u32<<<launch_blocks(h, ceil_div64(Gcap, 1024), 8), 256, 0, s>>>(present, Gcap, tot);
+  KERNEL_CHECK();
+  if (h->world > 1 && cl_local) comm_allreduce_int(h, tot.p, 1, 1, 0, s);
+  unsigned long long ht = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&ht, tot.p, sizeof(ht), cudaMemcpyDeviceToHost, s));
+  // meat = S'S (cross-rank: sum the score table for shared clusters, the k x k meats for rank-local ones)
+  DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
+  V.zero();
+  if (h->world > 1 && !cl_local) comm_allreduce(h, S, Gcap * k, 0, s);
+  std::vector<const double*> sc(k);
+  for (int c = 0; c < k; ++c) sc[c] = S.p + c;
+  gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, k);
+  if (h->world > 1 && cl_local) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
+  k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+  KERNEL_CHECK();
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  const int64_t G = (int64_t)ht;
+  if (n_clusters_out) n_clusters_out[0] = G;
+  LFE_REQUIRE(G > 1, "clustered vcov: a single cluster (division by zero in G/(G-1))");
+  double adj = (double)G / (double)(G - 1);
+  if (ssc) adj *= (double)(n_obs - 1) / (double)df_resid;
+  k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
+  KERNEL_CHECK();
+  h->n_launches += 7;
+}
+
 void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, const double* beta_full,
                      const double* Binv, int vcov_kind, const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W,
                      const double* weights, int ssc, int64_t n_obs, int64_t df_resid, double* se_out, double* vcov_out,
@@ -279,6 +392,11 @@ void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, co
   LFE_REQUIRE(vcov_kind >= 0 && vcov_kind <= 2, "lfe_resid_vcov: unknown vcov kind %d", vcov_kind);
   LFE_REQUIRE(n >= 1 || h->world > 1, "lfe_resid_vcov: no rows");
   if (vcov_kind == LFE_VCOV_CLUSTER) LFE_REQUIRE(W >= 1 && W <= LFE_MAX_CLUSTER_WAYS, "lfe_resid_vcov: cluster_cols required (1..%d ways)", LFE_MAX_CLUSTER_WAYS);
+  if (vcov_kind == LFE_VCOV_CLUSTER && W == 1 && k >= 1 && k <= PJ_MAXNC && !resid_out) {
+    fused_oneway_cluster(h, cols, k, n, beta_full, Binv, cl_codes[0], n_cl_groups[0], weights, ssc, n_obs, df_resid,
+                         cl_local, se_out, vcov_out, stats_out, n_clusters_out, s);
+    return;
+  }
   DevBuf<double> resid_buf;
   double* resid = resid_out;
   if (!resid) {
