@@ -263,8 +263,13 @@ def main():
 
     # ---- roofline of the demean sweep (dominant iterative kernel k_proj) -----------------------------
     C, F = K_REG + 1, 2
+    counters = {k_: v for k_, v in counters.items()}
     sweeps = res.iterations
-    sweep_ms = timers["demean_sweeps"] / args.steps / max(sweeps, 1)
+    # every k_proj launch (regular sweeps + the speculative first projection of the stopping test, which is the
+    # next sweep's first step) is timed by the library's CUDA events on the launching stream
+    proj_launches = max(counters["sweep_launches"] / args.steps, 1)
+    proj_ms = (timers["demean_sweeps"] + timers["demean_check"]) / args.steps / proj_launches
+    sweep_ms = F * proj_ms
     # bytes the coefficient-space sweep must move: per projection the FE-sorted int32 key + the other FE's code,
     # plus one read of S0 and one read-modify-write of alpha/acc per group row (SURVEY 8d 'read-only sweep' form)
     G_unit, G_time = n // ROWS_PER_UNIT, N_TIME
@@ -273,8 +278,12 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "k_proj<6,false> + k_finalize (one sweep = 2 projections)",
         "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak, "traffic": None,
+        "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak,
+        # ncu dram__bytes_read+write of the two k_proj launches of one sweep at this exact config
+        # (profiles/r1_ncu_top_kernels.md); null at other sizes
+        "traffic": 0.92e9 if (n == 50_000_000 and world == 1) else None,
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
+        "proj_launches_per_fit": proj_launches,
         "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
                                "frac": inplace_bytes / (sweep_ms / 1e3) / 1e9 / peak,
                                "note": "SURVEY 8(d) figure N*F*(16C+8) for the reference's in-place sweeps; this "

@@ -95,13 +95,14 @@ int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_gr
  * Replaces: `lf.filter(all_horizontal(len().over(fe) > 1))` polars_impl.py:478-482 (434-435).
  * keep_out[i] = 1 iff every FE's group of row i has more than one row; ONE pass on the input.
  * fe_dims_out[j] (nullable) = number of distinct codes of FE j among kept rows (:531-534).
- * n_keep_out[0] = kept rows on this rank, n_keep_out[1] = kept rows over all ranks.  With a
+ * n_keep_out[0] = kept rows on this rank, [1] = kept rows over all ranks, [2] = input rows over all
+ * ranks (so `[1] < [2]` is the same "something was dropped" decision on every rank).  With a
  * communicator attached, group sizes of every FE except `local_fe` (-1: none) are summed over the
  * ranks before the test and fe_dims are global.                                                  */
 int lfe_singleton_mask(lfe_handle h, const int32_t* const* codes, const int64_t* n_groups, int F,
                        int64_t n, int local_fe, const int32_t* const* counts /*nullable: rank-local group
                        sizes from lfe_group_counts, saves one pass per FE*/, uint8_t* keep_out,
-                       int64_t* n_keep_out /*[host] 2*/, int64_t* fe_dims_out /*[host] F*/, void* stream);
+                       int64_t* n_keep_out /*[host] 3*/, int64_t* fe_dims_out /*[host] F*/, void* stream);
 
 /* stable compaction of C double columns and K int32 columns by keep[]; outputs have n_keep rows */
 int lfe_compact(lfe_handle h, const uint8_t* keep, int64_t n,

@@ -274,7 +274,7 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         if n_obs == 0:
             raise ValueError("no observations left after dropping singleton groups (every row is alone in one of "
                              f"the fixed effects {fe_cols})")
-        if n_keep < codes[0].numel():
+        if n_obs < eng.last_n_rows_global:       # some rank dropped rows: every rank takes the compaction path
             y, X, x_cols, w = get_columns()
             k = len(X)
             f_in = [y] + X + ([w] if w is not None else [])

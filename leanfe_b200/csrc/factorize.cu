@@ -421,18 +421,19 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
   std::vector<unsigned long long> hacc(2 + F);
   CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  // rows over all ranks: "did anyone drop a row" must be ONE decision for every rank, here and in the caller
+  int64_t n_tot = n;
+  if (dist) {
+    DevBuf<unsigned long long> nt(1, s);
+    unsigned long long hn = (unsigned long long)n;
+    CUDA_CHECK(cudaMemcpyAsync(nt.p, &hn, sizeof(hn), cudaMemcpyHostToDevice, s));
+    comm_allreduce_int(h, nt.p, 1, 1, 0, s);
+    CUDA_CHECK(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    n_tot = (int64_t)hn;
+  }
+  n_keep_out[2] = n_tot;
   if (fe_dims_out) {
-    // `dropped` must be the same decision on every rank (collectives below)
-    int64_t n_tot = n;
-    if (dist) {
-      DevBuf<unsigned long long> nt(1, s);
-      unsigned long long hn = (unsigned long long)n;
-      CUDA_CHECK(cudaMemcpyAsync(nt.p, &hn, sizeof(hn), cudaMemcpyHostToDevice, s));
-      comm_allreduce_int(h, nt.p, 1, 1, 0, s);
-      CUDA_CHECK(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, s));
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      n_tot = (int64_t)hn;
-    }
     const bool dropped = (int64_t)hacc[1] < n_tot;
     for (int j = 0; j < F; ++j) {
       if (dropped) {  // a group survives iff it still has a kept row: one more pass over the codes

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(RS_T) k_radix_hist(const KeyT* __restrict__ ke
     if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&cnt[d], __popc(peers));
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < BINS; t += RS_T) hist[(size_t)t * nblocks + blockIdx.x] = cnt[t];
+  for (int t = threadIdx.x; t < BINS; t += RS_T) hist[(size_t)blockIdx.x * BINS + t] = cnt[t];   // block-major: coalesced
 }
 
 template <typename KeyT, int BITS>
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restric
       wcnt[w][t] = run;
       run += c;
     }
-    dbase[t] = offsets[(size_t)t * nblocks + blockIdx.x];
+    dbase[t] = offsets[(size_t)blockIdx.x * BINS + t];   // block-major copy of the scanned offsets: coalesced
   }
   __syncthreads();
 #pragma unroll
@@ -112,15 +112,35 @@ __global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restric
   }
 }
 
+// [rows][cols] -> [cols][rows] through a padded shared-memory tile (both sides coalesced)
+__global__ void __launch_bounds__(256) k_transpose_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                       int rows, int cols) {
+  __shared__ uint32_t tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < rows && bx + tx < cols) tile[r][tx] = in[(size_t)(by + r) * cols + bx + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < cols && by + tx < rows) out[(size_t)(bx + r) * rows + by + tx] = tile[tx][r];
+}
+
 template <typename KeyT, int BITS>
 static void radix_pass(lfe_ctx* h, const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout, int64_t n,
                        int shift, uint32_t* hist, int nblocks, cudaStream_t s) {
+  constexpr int BINS = 1 << BITS;
+  uint32_t* hist_t = hist + (size_t)BINS * nblocks;   // second half of the buffer: digit-major copy for the scan
   k_radix_hist<KeyT, BITS><<<nblocks, RS_T, 0, s>>>(kin, n, shift, hist, nblocks);
   KERNEL_CHECK();
-  prim_exclusive_scan_u32(h, hist, hist, (int64_t)(1 << BITS) * nblocks, nullptr, s);
+  dim3 g1((BINS + 31) / 32, (nblocks + 31) / 32), g2((nblocks + 31) / 32, (BINS + 31) / 32);
+  k_transpose_u32<<<g1, 256, 0, s>>>(hist, hist_t, nblocks, BINS);          // [block][digit] -> [digit][block]
+  KERNEL_CHECK();
+  prim_exclusive_scan_u32(h, hist_t, hist_t, (int64_t)BINS * nblocks, nullptr, s);
+  k_transpose_u32<<<g2, 256, 0, s>>>(hist_t, hist, BINS, nblocks);          // back to [block][digit]
+  KERNEL_CHECK();
   k_radix_scatter<KeyT, BITS><<<nblocks, RS_T, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
   KERNEL_CHECK();
-  h->n_launches += 2;
+  h->n_launches += 4;
 }
 
 // vals_in == nullptr -> payload = element index (argsort)
@@ -139,7 +159,7 @@ static void sort_pairs_impl(lfe_ctx* h, const KeyT* keys, const uint32_t* vals_i
   int bits = (key_bits + npass - 1) / npass;
   if (bits < 8) bits = 8;
   const int nblocks = (int)ceil_div64(n, RS_TILE);
-  DevBuf<uint32_t> hist((size_t)(1 << bits) * nblocks, s);
+  DevBuf<uint32_t> hist((size_t)2 * (1 << bits) * nblocks, s);
   DevBuf<KeyT> ka(npass > 1 ? n : 0, s), kb(npass > 2 ? n : 0, s);
   DevBuf<uint32_t> va(npass > 1 ? n : 0, s);
   const KeyT* kin = keys;

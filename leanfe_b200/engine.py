@@ -128,13 +128,14 @@ class Engine:
         self._check_dev(*codes)
         n = codes[0].numel()
         keep = self.empty(n, torch.uint8)
-        n_keep = (C.c_int64 * 2)()
+        n_keep = (C.c_int64 * 3)()
         dims = (C.c_int64 * len(codes))()
         capi.check(self.lib.lfe_singleton_mask(self.h, capi.ptr_array([c.data_ptr() for c in codes]),
                                                capi.i64_array(n_groups), len(codes), n, int(local_fe),
                                                capi.ptr_array([c.data_ptr() for c in counts]) if counts else None,
                                                self._p(keep), n_keep, dims, self.stream))
         self.last_n_keep_global = int(n_keep[1])
+        self.last_n_rows_global = int(n_keep[2])
         return keep, int(n_keep[0]), tuple(int(d) for d in dims)
 
     def compact(self, keep: torch.Tensor, n_keep: int, f64: list[torch.Tensor], i32: list[torch.Tensor]):

@@ -63,6 +63,30 @@ def main():
         if not ok:
             failures.append((vc, cl, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs, ref["n_obs"],
                              res.fe_dims, ref["fe_dims"], res.n_clusters, ref["n_clusters"]))
+    # three-way FE (worker = shard key, firm and year shared by all ranks), weighted, max_iter reached
+    nw, nf = 9000, 700
+    worker = rng.integers(0, nw, N)
+    firm = np.where(rng.random(N) < 0.8, rng.integers(0, nf, nw)[worker], rng.integers(0, nf, N))
+    year = rng.integers(0, 12, N)
+    wgt = rng.uniform(0.5, 2.0, N)
+    z1 = rng.normal(size=N)
+    yy = 0.4 * z1 + rng.normal(size=nw)[worker] + rng.normal(size=nf)[firm] + 0.1 * year + rng.normal(size=N)
+    full3 = dict(y=yy, z1=z1, worker=worker, firm=firm, year=year, wgt=wgt)
+    mine3 = shard_rows_by_key(worker, world)[rank]
+    shard3 = {k: v[mine3] for k, v in full3.items()}
+    for vc, cl, wname in (("hc1", None, None), ("iid", None, "wgt"), ("cluster", ["firm"], None)):
+        kw = dict(formula="y ~ z1 | worker + firm + year", vcov=vc, cluster_cols=cl, weights=wname, strategy="alt_proj",
+                  max_iter=12)
+        res = leanfe(shard3, local_fe="worker", **kw)
+        ref = O.leanfe_oracle(full3, **kw)
+        b, eb = np.array(list(res.coefs.values())), np.array(list(ref["coefs"].values()))
+        s, es = np.array(list(res.std_errors.values())), np.array(list(ref["std_errors"].values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.iterations == ref["iterations"] and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and tuple(res.fe_dims) == tuple(ref["fe_dims"]) and res.n_clusters == ref["n_clusters"])
+        if not ok:
+            failures.append(("3way", vc, cl, wname, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs,
+                             ref["n_obs"], res.fe_dims, ref["fe_dims"]))
     if rank == 0:
         print("multigpu_check:", "OK" if not failures else f"FAILED {failures}", f"(world={world})")
     dist.destroy_process_group()
