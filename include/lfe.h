@@ -147,7 +147,9 @@ int lfe_demean_plan_create(lfe_handle h, const int32_t* const* codes, const int6
                            int64_t n, const double* weights, int local_fe,
                            const int32_t* const* counts /*nullable, as in lfe_singleton_mask*/,
                            lfe_plan_t* plan_out, void* stream);
-int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, int C, const int* fe_order,
+int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols,
+                        const double* const* cols_src /*nullable: out of place, read from here, write to cols*/,
+                        int C, const int* fe_order,
                         double tol, int max_iter, int min_iter, int flags, int* iterations_out /*[host]*/,
                         double* max_mean_out /*[host]*/, int* converged_out /*[host]*/, void* stream);
 int lfe_demean_plan_destroy(lfe_handle h, lfe_plan_t plan);

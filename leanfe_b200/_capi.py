@@ -69,7 +69,7 @@ def load_library() -> C.CDLL:
     lib.lfe_demean.argtypes = [vp, P(vp), i32, P(vp), P(i64), P(i32), i32, i64, vp, dbl, i32, i32, i32, i32,
                                P(i32), P(dbl), P(i32), vp]
     lib.lfe_demean_plan_create.argtypes = [vp, P(vp), P(i64), i32, i64, vp, i32, P(vp), P(vp), vp]
-    lib.lfe_demean_plan_run.argtypes = [vp, vp, P(vp), i32, P(i32), dbl, i32, i32, i32, P(i32), P(dbl), P(i32), vp]
+    lib.lfe_demean_plan_run.argtypes = [vp, vp, P(vp), P(vp), i32, P(i32), dbl, i32, i32, i32, P(i32), P(dbl), P(i32), vp]
     lib.lfe_demean_plan_destroy.argtypes = [vp, vp]
     lib.lfe_gram.argtypes = [vp, P(vp), i32, i64, vp, i32, vp, vp]
     lib.lfe_solve_spd.argtypes = [vp, vp, vp, i32, vp, vp, P(i32), vp]

@@ -299,14 +299,14 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
 
             def fetch(name):
                 t = lazy["get"](name)
-                return t if own(t) else t.clone()                             # never overwrite caller-owned data
+                return (t, None) if own(t) else (torch.empty_like(t), [t])    # never overwrite caller-owned data
 
-            ycol = fetch(lazy["y"])
-            iterations, _, converged = plan.run([ycol], order, tol, max_iter, 3)
+            ycol, ysrc = fetch(lazy["y"])
+            iterations, _, converged = plan.run([ycol], order, tol, max_iter, 3, src=ysrc)
             cols, x_cols = [ycol], list(lazy["x"])
             for name in x_cols:
-                c = fetch(name)
-                plan.run([c], order, tol, iterations, iterations + 1)         # T sweeps, no stopping test
+                c, csrc = fetch(name)
+                plan.run([c], order, tol, iterations, iterations + 1, src=csrc)   # T sweeps, no stopping test
                 cols.append(c)
             k = len(x_cols)
             absorbed = sum(fe_dims) - F
@@ -315,13 +315,18 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
                 y, X, x_cols, w = get_columns()
                 k = len(X)
                 own = getattr(get_columns, "owned", lambda t: False)
-                cols = [c if own(c) else c.clone() for c in [y] + X]   # in place, but never on caller-owned data
+                src = [y] + X
+                # caller-owned device columns are read in place and the demeaned values written to fresh buffers
+                cols = [c if own(c) else torch.empty_like(c) for c in src]
+            else:
+                src = cols
+            src_arg = None if all(a is b for a, b in zip(src, cols)) else src
             if strategy == "demean":
-                plan.run(cols, order, tol, 1, 2)
+                plan.run(cols, order, tol, 1, 2, src=src_arg)
                 iterations, converged = 1, True
                 absorbed = fe_dims[0] - 1
             else:
-                iterations, _, converged = plan.run(cols, order, tol, max_iter, 3)
+                iterations, _, converged = plan.run(cols, order, tol, max_iter, 3, src=src_arg)
                 absorbed = sum(fe_dims) - F
         plan.close()
     else:

@@ -21,9 +21,9 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
                  cudaStream_t s);
 lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
                              const double* weights, int local_fe, const int32_t* const* counts_in, cudaStream_t s);
-void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, const int* fe_order, double tol,
-                     int max_iter, int min_iter, int flags, int* iterations_out, double* max_mean_out,
-                     int* converged_out, cudaStream_t s);
+void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const double* const* cols_src, int C,
+                     const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
+                     double* max_mean_out, int* converged_out, cudaStream_t s);
 void demean_plan_destroy(lfe_plan* plan);
 void gram_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* weights, int add_intercept,
                double* gram_out, cudaStream_t s);
@@ -294,13 +294,13 @@ int lfe_demean_plan_create(lfe_handle h, const int32_t* const* codes, const int6
   *plan_out = demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, counts, S(stream));
   LFE_API_END
 }
-int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, int C, const int* fe_order, double tol,
-                        int max_iter, int min_iter, int flags, int* iterations_out, double* max_mean_out,
-                        int* converged_out, void* stream) {
+int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, const double* const* cols_src, int C,
+                        const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
+                        double* max_mean_out, int* converged_out, void* stream) {
   LFE_API_BEGIN
   LFE_REQUIRE(h && plan && cols && fe_order && iterations_out, "lfe_demean_plan_run: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
-  demean_plan_run(h, plan, cols, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
+  demean_plan_run(h, plan, cols, cols_src, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
                   converged_out, S(stream));
   LFE_API_END
 }

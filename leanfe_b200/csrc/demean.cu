@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_apply(MutColPtrs cols, ApplyTabs T, int
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      double x = __ldcs(cols.col[c] + i);
+      double x = __ldcs(cols.src[c] + i);
       __stcs(cols.col[c] + i, x - s[c]);
     }
   }
@@ -487,9 +487,14 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
 
 void demean_plan_destroy(lfe_plan* plan) { delete plan; }
 
-void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, const int* fe_order, double tol,
-                     int max_iter, int min_iter, int flags, int* iterations_out, double* max_mean_out,
-                     int* converged_out, cudaStream_t s) {
+// cols_src (nullable): read the input columns from there and write the demeaned columns to `cols`
+// (out of place: the caller's data stay untouched without a separate copy); nullptr = in place on `cols`.
+void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const double* const* cols_src, int C,
+                     const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
+                     double* max_mean_out, int* converged_out, cudaStream_t s) {
+  std::vector<const double*> src_v(C);
+  for (int c = 0; c < C; ++c) src_v[c] = cols_src ? cols_src[c] : cols[c];
+  const double* const* in = src_v.data();
   const bool strict_check = (flags & LFE_DEMEAN_STRICT_CHECK) != 0;
   const int F = plan->F;
   const int64_t n = plan->n;
@@ -532,7 +537,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
       for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
         int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
         ColPtrs cp;
-        for (int c = 0; c < nc; ++c) cp.col[c] = cols[c0 + c];
+        for (int c = 0; c < nc; ++c) cp.col[c] = in[c0 + c];
         if (weighted) launch_groupsum<true>(h, nc, codes[j], S.G, cp, weights, n, S.S0, C, c0, s);
         else launch_groupsum<false>(h, nc, codes[j], S.G, cp, nullptr, n, S.S0, C, c0, s);
       }
@@ -540,7 +545,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
         // unweighted y sums for the convergence check (polars_impl.py:513 ignores the weights)
         S.S0u_buf.alloc(S.G, s);
         S.S0u_buf.zero();
-        ColPtrs cy; cy.col[0] = cols[0];
+        ColPtrs cy; cy.col[0] = in[0];
         launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
         S.S0u = S.S0u_buf; S.ld_s0u = 1;
       } else {
@@ -697,7 +702,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, int C, con
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
       MutColPtrs mp;
-      for (int c = 0; c < nc; ++c) mp.col[c] = cols[c0 + c];
+      for (int c = 0; c < nc; ++c) { mp.col[c] = cols[c0 + c]; mp.src[c] = in[c0 + c]; }
       if (n > 0) launch_apply(h, nc, mp, T, n, C, c0, apply_smem, s);
     }
   }
@@ -711,6 +716,6 @@ void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* c
                  int local_fe, int flags, int* iterations_out, double* max_mean_out, int* converged_out,
                  cudaStream_t s) {
   std::unique_ptr<lfe_plan> plan(demean_plan_create(h, codes, n_groups, F, n, weights, local_fe, nullptr, s));
-  demean_plan_run(h, plan.get(), cols, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
-                  converged_out, s);
+  demean_plan_run(h, plan.get(), cols, nullptr, C, fe_order, tol, max_iter, min_iter, flags, iterations_out,
+                  max_mean_out, converged_out, s);
 }

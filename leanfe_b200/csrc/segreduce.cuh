@@ -33,7 +33,8 @@ struct ColPtrs {
   const double* col[PJ_MAXNC];
 };
 struct MutColPtrs {
-  double* col[PJ_MAXNC];
+  double* col[PJ_MAXNC];         // destination
+  const double* src[PJ_MAXNC];   // source (== col for in-place)
 };
 
 __device__ __forceinline__ void load4_i32(const int32_t* __restrict__ p, int64_t base, int64_t n, bool vec, int out[4]) {

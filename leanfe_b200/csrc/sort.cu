@@ -56,9 +56,11 @@ __global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restric
                                                         int64_t n, int shift, const uint32_t* __restrict__ offsets,
                                                         int nblocks) {
   constexpr int BINS = 1 << BITS;
-  __shared__ uint32_t wcnt[RS_NW][BINS];
-  __shared__ uint32_t dbase[BINS];
-  for (int i = threadIdx.x; i < RS_NW * BINS; i += RS_T) (&wcnt[0][0])[i] = 0;
+  __shared__ __align__(16) uint32_t wcnt[RS_NW][BINS];
+  {
+    uint4* z = reinterpret_cast<uint4*>(&wcnt[0][0]);   // 128-bit zero fill
+    for (int i = threadIdx.x; i < RS_NW * BINS / 4; i += RS_T) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -90,14 +92,14 @@ __global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restric
   }
   __syncthreads();
   for (int t = threadIdx.x; t < BINS; t += RS_T) {
-    uint32_t run = 0;
+    // absolute output base of (warp, digit): global digit offset of this tile + the earlier warps' counts
+    uint32_t run = offsets[(size_t)blockIdx.x * BINS + t];   // block-major copy of the scanned offsets: coalesced
 #pragma unroll
     for (int w = 0; w < RS_NW; ++w) {
       uint32_t c = wcnt[w][t];
       wcnt[w][t] = run;
       run += c;
     }
-    dbase[t] = offsets[(size_t)blockIdx.x * BINS + t];   // block-major copy of the scanned offsets: coalesced
   }
   __syncthreads();
 #pragma unroll
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(RS_T, 3) k_radix_scatter(const KeyT* __restric
     int64_t idx = wbase + r * 32 + lane;
     if (idx < n) {
       uint32_t d = (uint32_t)((k[r] >> shift) & (BINS - 1));
-      uint32_t pos = dbase[d] + wcnt[warp][d] + rk[r];
+      uint32_t pos = wcnt[warp][d] + rk[r];
       if (keys_out) keys_out[pos] = k[r];
       vals_out[pos] = v[r];
     }

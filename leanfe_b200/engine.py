@@ -339,15 +339,20 @@ class DemeanPlan:
         self.p = p
 
     def run(self, cols: list[torch.Tensor], fe_order: list[int], tol: float = 1e-6, max_iter: int = 50,
-            min_iter: int = 3, strict_check: bool = False):
-        """In place on ``cols`` (cols[0] = y).  -> (iterations, max_mean, converged)"""
+            min_iter: int = 3, strict_check: bool = False, src: list[torch.Tensor] | None = None):
+        """Demean ``cols`` (cols[0] = y) in place, or -- with ``src`` -- read the inputs from ``src`` and write the
+        demeaned columns to ``cols`` (caller data untouched, no extra copy).  -> (iterations, max_mean, converged)"""
         eng = self.eng
-        eng._check_dev(*cols)
+        eng._check_dev(*cols, *(src or []))
+        if src is not None and (len(src) != len(cols) or any(t.dtype != torch.float64 or t.numel() != self.n for t in src)):
+            raise ValueError("src must match cols (float64, one value per plan row)")
         for t in cols:
             if t.dtype != torch.float64 or t.numel() != self.n:
                 raise ValueError("demean columns must be float64 with one value per plan row")
         it, mm, cv = C.c_int(0), C.c_double(0.0), C.c_int(0)
-        capi.check(eng.lib.lfe_demean_plan_run(eng.h, self.p, capi.ptr_array([t.data_ptr() for t in cols]), len(cols),
+        capi.check(eng.lib.lfe_demean_plan_run(eng.h, self.p, capi.ptr_array([t.data_ptr() for t in cols]),
+                                               capi.ptr_array([t.data_ptr() for t in src]) if src is not None else None,
+                                               len(cols),
                                                capi.i32_array(fe_order), float(tol), int(max_iter), int(min_iter),
                                                1 if strict_check else 0, C.byref(it), C.byref(mm), C.byref(cv),
                                                eng.stream))

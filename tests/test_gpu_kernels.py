@@ -398,3 +398,23 @@ def test_every_row_its_own_group_and_one_group(eng):
         assert float(got.abs().max()) < 1e-12
     keep, n_keep, dims = eng.singleton_mask([dev(a), dev(b)], [n, 1])
     assert n_keep == 0 and dims == (0, 0) and int(keep.sum()) == 0
+
+
+def test_demean_plan_out_of_place_matches_in_place(eng):
+    """lfe_demean_plan_run with cols_src: inputs untouched, outputs identical to the in-place run."""
+    rng = np.random.default_rng(11)
+    n = 40_000
+    Gs = (900, 17)
+    codes = [dev(rng.integers(0, g, n).astype(np.int32)) for g in Gs]
+    src = [dev(rng.normal(size=n)) for _ in range(3)]
+    keep = [t.clone() for t in src]
+    plan = eng.demean_plan(codes, list(Gs))
+    a = [t.clone() for t in src]
+    it_a = plan.run(a, [1, 0], 1e-10, 100, 3)
+    b = [torch.full_like(t, float("nan")) for t in src]
+    it_b = plan.run(b, [1, 0], 1e-10, 100, 3, src=src)
+    plan.close()
+    assert it_a[0] == it_b[0] and it_a[2] == it_b[2]
+    for x, y_, s0, k0 in zip(a, b, src, keep):
+        assert torch.equal(s0, k0)
+        assert float((x - y_).abs().max()) < 1e-12        # fp64 atomics: summation order differs run to run
