@@ -184,15 +184,36 @@ int lfe_resid_vcov(lfe_handle h, const double* const* cols, int k, int64_t n,
 /* ---- (3) YOCO compression ---------------------------------------------------------------------
  * Replaces: lf.group_by(x_cols + fe_cols + cluster_cols).agg(len, sum y, sum y^2)
  * compress.py:325-350 and the distinct count of estimate_compression_ratio compress.py:249-250.
- * key_codes: K int32 code columns (from lfe_factorize, order 0) with cardinalities n_groups[K].
+ * key_codes: K code columns with cardinalities n_groups[K]: int32 codes from lfe_factorize (order 0), or --
+ * key_dtypes[j] == LFE_U8 -- raw uint8 values used as codes (dummies; n_groups[j] = max + 1 from
+ * lfe_key_ranges, no factorisation pass).  key_dtypes NULL = all LFE_I32.
  * Groups are emitted in ascending lexicographic order of the code tuples.  Outputs have capacity
  * out_cap rows: key_codes_out[K] (int32), n_out (sum of weights, or count), cnt_out (int32 raw
  * count), sum_y_out, sum_y_sq_out.  y may be NULL (count-distinct only; stats outputs NULL).     */
-int lfe_compress(lfe_handle h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
-                 const double* y, const double* weights, int64_t n, int64_t out_cap,
+int lfe_compress(lfe_handle h, const void* const* key_codes, const int* key_dtypes /*nullable*/,
+                 const int64_t* n_groups, int K, const double* y, const double* weights, int64_t n, int64_t out_cap,
                  int32_t* const* key_codes_out, double* n_out, int32_t* cnt_out,
                  double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out /*[host]*/,
                  void* stream);
+
+/* [min, max] of K integer key columns (LFE_U8 / LFE_I32 / LFE_I64) in one call; with a communicator attached,
+ * of the whole sharded columns.  An empty column reports min = INT64_MAX, max = INT64_MIN.  Serves the
+ * key-cardinality bookkeeping of compress.py:232-253, 334-336 for columns that need no dictionary.   */
+int lfe_key_ranges(lfe_handle h, const void* const* cols, const int* dtypes, int K, int64_t n,
+                   int64_t* min_out /*[host] K*/, int64_t* max_out /*[host] K*/, void* stream);
+
+/* Multi-GPU YOCO: rows are sharded arbitrarily, every rank runs lfe_compress on its own rows
+ * (key codes from ONE shared code space: lfe_factorize with LFE_ORDER_GLOBAL), then this call all-gathers the
+ * partial tables (n_rows rows on this rank) and re-aggregates them: every rank receives the identical global
+ * table, groups in ascending lexicographic order, with n / cnt / sum_y / sum_y_sq summed over ranks.  Replaces
+ * nothing in the reference (single process); it is what makes compress.py:325-350 shard.  Without a
+ * communicator it merges duplicate keys inside the one table given.                                */
+int lfe_compress_merge(lfe_handle h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
+                       const double* n_in, const int32_t* cnt_in, const double* sum_y_in,
+                       const double* sum_y_sq_in, int64_t n_rows, int64_t out_cap,
+                       int32_t* const* key_codes_out, double* n_out, int32_t* cnt_out /*nullable*/,
+                       double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out /*[host]*/,
+                       void* stream);
 
 /* ---- YOCO standard errors --------------------------------------------------------------------
  * Replaces: compute_rss_grouped compress.py:754-810, e0_g compress.py:1124-1137 and compute_se_compress
@@ -213,6 +234,9 @@ int lfe_yoco_vcov(lfe_handle h, const double* const* cols, int k, int64_t n_comp
 int lfe_comm_unique_id(void* id_out /*[host] 128 bytes*/);
 int lfe_comm_init(lfe_handle h, const void* id /*[host] 128 bytes*/, int rank, int world);
 int lfe_comm_destroy(lfe_handle h);
+/* active = 0: the calls that follow run rank-locally (no collectives) although a communicator is attached --
+ * used for work that is replicated on every rank, e.g. the solve on the merged YOCO table; 1 = back on. */
+int lfe_comm_set_active(lfe_handle h, int active);
 /* sum all-reduce of a device double buffer over the attached communicator (no-op if none) */
 int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream);
 

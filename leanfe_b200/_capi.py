@@ -27,7 +27,8 @@ EXPORTS = [
     "lfe_get_timers", "lfe_get_counters", "lfe_factorize", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
     "lfe_sort_rows", "lfe_gather", "lfe_demean", "lfe_demean_plan_create", "lfe_demean_plan_run",
     "lfe_demean_plan_destroy", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
-    "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_allreduce_f64",
+    "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
+    "lfe_allreduce_f64",
 ]
 
 
@@ -75,12 +76,15 @@ def load_library() -> C.CDLL:
     lib.lfe_solve_spd.argtypes = [vp, vp, vp, i32, vp, vp, P(i32), vp]
     lib.lfe_resid_vcov.argtypes = [vp, P(vp), i32, i64, vp, vp, i32, P(vp), P(i64), i32, vp, i32, i64, i64,
                                    vp, vp, vp, vp, P(i64), vp]
-    lib.lfe_compress.argtypes = [vp, P(vp), P(i64), i32, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
+    lib.lfe_compress.argtypes = [vp, P(vp), P(i32), P(i64), i32, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
+    lib.lfe_key_ranges.argtypes = [vp, P(vp), P(i32), i32, i64, P(i64), P(i64), vp]
     lib.lfe_yoco_vcov.argtypes = [vp, P(vp), i32, i64, vp, vp, vp, vp, vp, i32, P(vp), P(i64), i32, i32, i64, i64,
                                   vp, vp, vp, P(i64), vp]
     lib.lfe_comm_unique_id.argtypes = [vp]
     lib.lfe_comm_init.argtypes = [vp, vp, i32, i32]
     lib.lfe_comm_destroy.argtypes = [vp]
+    lib.lfe_comm_set_active.argtypes = [vp, i32]
+    lib.lfe_compress_merge.argtypes = [vp, P(vp), P(i64), i32, vp, vp, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
     lib.lfe_allreduce_f64.argtypes = [vp, vp, i64, vp]
     for name in EXPORTS:
         if name not in ("lfe_last_error",):

@@ -9,6 +9,7 @@ the strategy rule actually needs it.
 """
 from __future__ import annotations
 
+import contextlib
 import time
 
 import numpy as np
@@ -102,14 +103,17 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     frame = Frame(data, needed)
     dist = eng.world > 1
     if dist:
-        if local_fe is None or local_fe not in fe_cols:
+        if strategy not in ("alt_proj", "demean", "compress"):
+            raise NotImplementedError("multi-GPU fits support strategy='alt_proj' / 'demean' / 'compress' "
+                                      "(pass it explicitly)")
+        if strategy == "compress":
+            local_fe = None          # YOCO shards rows arbitrarily: every key column uses the shared code space
+        elif local_fe is None or local_fe not in fe_cols:
             raise ValueError("multi-GPU fit: pass local_fe=<the FE column rows are sharded by>")
-        if strategy not in ("alt_proj", "demean"):
-            raise NotImplementedError("multi-GPU fits support strategy='alt_proj' / 'demean' (pass it explicitly)")
         if sample_frac is not None:
             raise NotImplementedError("sample_frac is not supported in multi-GPU fits")
-        if cluster_cols and len(cluster_cols) > 1:
-            raise NotImplementedError("multi-way clustering is single-GPU only")
+        if cluster_cols and len(cluster_cols) > 1 and strategy != "compress":
+            raise NotImplementedError("multi-way clustering is single-GPU only (except strategy='compress')")
 
     # every H2D copy is enqueued now, ids first: the id-only work below overlaps the fp64 uploads
     key_first = fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions] + [v for v, _ in factor_vars]
@@ -358,15 +362,31 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
 
 
 def _fit_compress(eng: Engine, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n_obs):
-    """YOCO (compress.py:1049-1174): device group-by, then FWL on the compressed rows."""
+    """YOCO (compress.py:1049-1174): device group-by, then FWL on the compressed rows.
+
+    Multi-GPU: each rank groups its own rows -- all key columns coded in one shared code space --
+    the partial tables are all-gathered and re-aggregated (``lfe_compress_merge``), and the small solve on the
+    merged table is repeated identically on every rank (no collectives inside)."""
     k, F = len(X), len(fe_keys)
     if k == 0:
         raise ValueError("strategy='compress' needs at least one regressor")
+    dist = eng.world > 1
+    if dist:
+        n_obs = int(eng.allreduce(torch.tensor([float(n_obs)], dtype=torch.float64, device=eng.device)).item())
     group_names = x_cols + fe_cols
-    xk = []
-    for c in X:
-        codes, G, uniq = eng.factorize(c, want_uniques=True, uniques_cap=1 << 20)
-        xk.append((codes, G, uniq.to(torch.float64)))
+    xk = [None] * k
+    x_order = capi.ORDER_SORTED | (capi.ORDER_GLOBAL if dist else 0)
+    # uint8 regressors (dummies, treatment x period indicators) are grouped on their raw values, 1 byte per row:
+    # no dictionary pass, value of code c is c itself
+    raw = [j for j, c in enumerate(X) if c.dtype == torch.uint8 and c.is_contiguous()]
+    if raw:
+        for j, (_, hi) in zip(raw, eng.key_ranges([X[j] for j in raw])):
+            radix = max(int(hi), 0) + 1
+            xk[j] = (X[j], radix, torch.arange(radix, dtype=torch.float64, device=eng.device))
+    for j, c in enumerate(X):
+        if xk[j] is None:
+            codes, G, uniq = eng.factorize(c, x_order, want_uniques=True, uniques_cap=1 << 20)
+            xk[j] = (codes, G, uniq.to(torch.float64))
     kc = [(c, G) for c, G, _ in xk] + [(f.codes, f.n_groups) for f in fe_keys]
     cl_idx = []
     for name, ck in zip(cluster_cols or [], cl_keys):
@@ -377,28 +397,44 @@ def _fit_compress(eng: Engine, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_
             kc.append((ck.codes, ck.n_groups))
             cl_idx.append(len(kc) - 1)
     comp = eng.compress([c for c, _ in kc], [g for _, g in kc], y, w)
-    G = comp["n_compressed"]
-    kout = comp["key_codes"]
-    # regressor values of each compressed row = uniques[code]; group means; weights n_g
-    Xg = [xk[j][2].index_select(0, kout[j].long()).contiguous() for j in range(k)]
-    nn, sy, syy = comp["n"], comp["sum_y"], comp["sum_y_sq"]
-    cols = [(sy / nn).contiguous()] + Xg
-    fe_codes = [kout[k + j] for j in range(F)]
-    fe_G = [f.n_groups for f in fe_keys]
-    fe_dims = tuple(fe_G) if F else None
-    # no FE: the intercept alone is absorbed, i.e. one "fixed effect" with a single level
-    dm_codes = fe_codes if F else [torch.zeros(G, dtype=torch.int32, device=eng.device)]
-    dm_G = fe_G if F else [1]
-    scale = float(torch.max(torch.abs(cols[0])).item()) + 1.0
-    order = sorted(range(len(dm_G)), key=lambda j: dm_G[j])
-    eng.demean(cols, dm_codes, dm_G, order, nn, 1e-14 * scale, 20000, 1, strict_check=True)
-    gram = eng.gram(cols[1:] + [cols[0]], nn, add_intercept=False)
-    beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
-    p = 1 + k + sum(g - 1 for g in fe_G)
-    df_resid = n_obs - p
-    out = eng.yoco_vcov(cols, beta, B, nn, sy, syy, vkind, [kout[i] for i in cl_idx], [kc[i][1] for i in cl_idx],
-                        ssc, n_obs, df_resid)
-    host = torch.cat([beta, out["se"], out["rss"]]).cpu().numpy()
+    if dist:
+        comp = eng.compress_merge(comp, [g for _, g in kc])
+    return _solve_compressed(eng, comp, xk, kc, cl_idx, x_cols, fe_keys, k, F, vcov, vkind, ssc, n_obs, dist)
+
+
+def _solve_compressed(eng: Engine, comp, xk, kc, cl_idx, x_cols, fe_keys, k, F, vcov, vkind, ssc, n_obs, dist=False):
+    """Weighted FWL + YOCO standard errors on the compressed table (compress.py:503-1042, 1105-1174).
+
+    ``dist``: the table is the merged one, identical on every rank; the solve runs rank-locally on each of
+    them and rank 0's numbers are then shared, so all ranks return bit-identical results."""
+    with (eng.replicated() if dist else contextlib.nullcontext()):
+        G = comp["n_compressed"]
+        kout = comp["key_codes"]
+        # regressor values of each compressed row = uniques[code]; group means; weights n_g
+        Xg = [xk[j][2].index_select(0, kout[j].long()).contiguous() for j in range(k)]
+        nn, sy, syy = comp["n"], comp["sum_y"], comp["sum_y_sq"]
+        cols = [(sy / nn).contiguous()] + Xg
+        fe_codes = [kout[k + j] for j in range(F)]
+        fe_G = [f.n_groups for f in fe_keys]
+        fe_dims = tuple(fe_G) if F else None
+        # no FE: the intercept alone is absorbed, i.e. one "fixed effect" with a single level
+        dm_codes = fe_codes if F else [torch.zeros(G, dtype=torch.int32, device=eng.device)]
+        dm_G = fe_G if F else [1]
+        scale = float(torch.max(torch.abs(cols[0])).item()) + 1.0
+        order = sorted(range(len(dm_G)), key=lambda j: dm_G[j])
+        eng.demean(cols, dm_codes, dm_G, order, nn, 1e-14 * scale, 20000, 1, strict_check=True)
+        gram = eng.gram(cols[1:] + [cols[0]], nn, add_intercept=False)
+        beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
+        p = 1 + k + sum(g - 1 for g in fe_G)
+        df_resid = n_obs - p
+        out = eng.yoco_vcov(cols, beta, B, nn, sy, syy, vkind, [kout[i] for i in cl_idx], [kc[i][1] for i in cl_idx],
+                            ssc, n_obs, df_resid)
+        dev = torch.cat([beta, out["se"], out["rss"]])
+    if dist:
+        if eng.rank != 0:
+            dev.zero_()
+        eng.allreduce(dev)
+    host = dev.cpu().numpy()
     n_clusters = None
     if vkind == capi.VCOV_CLUSTER:
         n_clusters = out["n_clusters"][0] if len(cl_idx) == 1 else tuple(out["n_clusters"])

@@ -38,10 +38,17 @@ void yoco_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t G, con
                     const int32_t* const* cl_codes, const int64_t* n_cl_groups, int W, int ssc, int64_t n_obs,
                     int64_t df_resid, double* se_out, double* vcov_out, double* rss_out, int64_t* n_clusters_out,
                     cudaStream_t s);
-void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n_groups, int K, const double* y,
-                   const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
-                   int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
+void compress_impl(lfe_ctx* h, const void* const* key_codes, const int* key_dtypes, const int64_t* n_groups, int K,
+                   const double* y, const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out,
+                   double* n_out, int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
                    cudaStream_t s);
+void key_ranges_impl(lfe_ctx* h, const void* const* cols, const int* dtypes, int K, int64_t n, int64_t* min_out,
+                     int64_t* max_out, cudaStream_t s);
+void compress_merge_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
+                         const double* n_in, const int32_t* cnt_in, const double* sum_y_in, const double* sum_y_sq_in,
+                         int64_t n_rows, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
+                         int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
+                         cudaStream_t s);
 
 // ---- errors ---------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -142,10 +149,11 @@ void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStre
   if (h->world <= 1 || count <= 0) return;
   NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, NCCL_FLOAT64, op_max ? NCCL_MAX : NCCL_SUM, h->nccl_comm, s));
 }
-// kind: 0 = uint32, 1 = uint64 ; op: 0 sum, 2 max, 3 min (NCCL numbering)
+// kind: 0 = uint32, 1 = uint64, 2 = int64 ; op: 0 sum, 2 max, 3 min (NCCL numbering)
 void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s) {
   if (h->world <= 1 || count <= 0) return;
-  NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, kind == 0 ? 3 : 5, op, h->nccl_comm, s));
+  const int nccl_type = kind == 0 ? 3 : (kind == 1 ? 5 : 4);
+  NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, nccl_type, op, h->nccl_comm, s));
 }
 
 // ---- exported functions -------------------------------------------------------------------------------
@@ -341,14 +349,36 @@ int lfe_resid_vcov(lfe_handle h, const double* const* cols, int k, int64_t n, co
   LFE_API_END
 }
 
-int lfe_compress(lfe_handle h, const int32_t* const* key_codes, const int64_t* n_groups, int K, const double* y,
-                 const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
-                 int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out, void* stream) {
+int lfe_compress(lfe_handle h, const void* const* key_codes, const int* key_dtypes, const int64_t* n_groups, int K,
+                 const double* y, const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out,
+                 double* n_out, int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
+                 void* stream) {
   LFE_API_BEGIN
   LFE_REQUIRE(h && n_compressed_out && (K == 0 || (key_codes && n_groups)), "lfe_compress: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
-  compress_impl(h, key_codes, n_groups, K, y, weights, n, out_cap, key_codes_out, n_out, cnt_out, sum_y_out,
-                sum_y_sq_out, n_compressed_out, S(stream));
+  compress_impl(h, key_codes, key_dtypes, n_groups, K, y, weights, n, out_cap, key_codes_out, n_out, cnt_out,
+                sum_y_out, sum_y_sq_out, n_compressed_out, S(stream));
+  LFE_API_END
+}
+
+int lfe_key_ranges(lfe_handle h, const void* const* cols, const int* dtypes, int K, int64_t n, int64_t* min_out,
+                   int64_t* max_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && cols && dtypes && min_out && max_out && n >= 0, "lfe_key_ranges: bad argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  key_ranges_impl(h, cols, dtypes, K, n, min_out, max_out, S(stream));
+  LFE_API_END
+}
+
+int lfe_compress_merge(lfe_handle h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
+                       const double* n_in, const int32_t* cnt_in, const double* sum_y_in, const double* sum_y_sq_in,
+                       int64_t n_rows, int64_t out_cap, int32_t* const* key_codes_out, double* n_out, int32_t* cnt_out,
+                       double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && n_compressed_out && key_codes && n_groups, "lfe_compress_merge: NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  compress_merge_impl(h, key_codes, n_groups, K, n_in, cnt_in, sum_y_in, sum_y_sq_in, n_rows, out_cap, key_codes_out,
+                      n_out, cnt_out, sum_y_out, sum_y_sq_out, n_compressed_out, S(stream));
   LFE_API_END
 }
 
@@ -383,6 +413,13 @@ int lfe_comm_init(lfe_handle h, const void* id, int rank, int world) {
   NCCL_CHECK(g_nccl.init_rank(&h->nccl_comm, world, uid, rank));
   h->rank = rank;
   h->world = world;
+  h->world_attached = world;
+  LFE_API_END
+}
+int lfe_comm_set_active(lfe_handle h, int active) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h != nullptr, "lfe_comm_set_active: handle is NULL");
+  h->world = (active && h->nccl_comm) ? h->world_attached : 1;
   LFE_API_END
 }
 int lfe_comm_destroy(lfe_handle h) {
@@ -390,6 +427,7 @@ int lfe_comm_destroy(lfe_handle h) {
   if (h->nccl_comm) NCCL_CHECK(g_nccl.destroy(h->nccl_comm));
   h->nccl_comm = nullptr;
   h->world = 1;
+  h->world_attached = 1;
   h->rank = 0;
   LFE_API_END
 }

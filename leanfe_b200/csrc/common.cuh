@@ -63,6 +63,7 @@ struct lfe_ctx {
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  int world_attached = 1;   // size of the attached communicator; world == 1 while collectives are suspended
 };
 
 // RAII phase timer: records a CUDA-event pair on the stream when profiling is on.

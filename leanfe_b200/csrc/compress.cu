@@ -5,8 +5,10 @@
 // The K code columns are folded into a mixed-radix key (most significant = first column, so ascending key
 // order == ascending lexicographic order of the code tuples) and the key is factorised.  Folding is STAGED:
 // columns are accumulated while the product of their cardinalities stays below 2^26, then that partial key
-// is replaced by its dense sorted rank (direct-address table, three streaming passes) before more columns
-// are folded in.  Ranks are order-preserving, so the final group order is still lexicographic, and the
+// is replaced by its dense sorted rank before more columns are folded in: a direct-address presence table,
+// filled and read back by two passes that RECOMPUTE the folded key from the raw columns (k_fold_mark /
+// k_fold_lookup), so the 64-bit keys are never written to memory.  uint8 columns (dummies) enter as they are,
+// 1 byte per row, without a factorisation pass.  Ranks are order-preserving, so the final group order is still lexicographic, and the
 // composite key of, e.g., 23 dummies x 1000 groups x 24 periods (2e11 combinations, 24 000 present) never
 // needs a 38-bit radix sort.  Counts / sum w / sum w y / sum w y^2 are by-key reductions.  Keys and counts
 // are exact integers, hence bit-reproducible; the floating sums differ from a sequential group-by only by
@@ -23,17 +25,119 @@ constexpr int CP_MAXK = 32;
 constexpr unsigned long long CP_STAGE_SPACE = 1ull << 26;
 
 struct KeyCols {
-  const int32_t* code[CP_MAXK + 1];
-  unsigned long long radix[CP_MAXK + 1];
-  int K;
+  // u8 columns first (n_u8 of them), int32 code columns after; mult[j] = product of the radices of the
+  // columns that FOLLOW column j in the caller's order, so key = sum_j value_j * mult[j] in any order
+  const void* col[CP_MAXK + 1];
+  unsigned long long mult[CP_MAXK + 1];
+  int n_u8, K;
 };
 
-__global__ void __launch_bounds__(256) k_fold_keys(KeyCols kc, int64_t n, uint64_t* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    unsigned long long key = 0;
-    for (int j = 0; j < kc.K; ++j) key = key * kc.radix[j] + (unsigned long long)__ldcs(kc.code[j] + i);
-    out[i] = key;
+constexpr int FR = 16;   // consecutive rows per thread: one 128-bit load per uint8 column, four per int32 column
+
+// Folded keys of FR consecutive rows (q = row / FR).  KT = unsigned (direct-address stages, key space <= 2^26)
+// or unsigned long long.  Loads are issued four columns at a time before they are consumed, so every thread
+// keeps 64 bytes in flight.
+template <typename KT>
+__device__ __forceinline__ void acc_u8x16(KT key[FR], const uint4& t, KT m) {
+  const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) key[4 * a + b] += (KT)((w[a] >> (8 * b)) & 0xffu) * m;
+}
+template <typename KT>
+__device__ __forceinline__ void fold_rows(const KeyCols& kc, int64_t q, int64_t n, bool vec, KT key[FR]) {
+  const int64_t base = q * FR;
+#pragma unroll
+  for (int e = 0; e < FR; ++e) key[e] = 0;
+  if (vec && base + FR - 1 < n) {
+    int j = 0;
+    for (; j + 4 <= kc.n_u8; j += 4) {
+      uint4 t0 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j]) + q);
+      uint4 t1 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 1]) + q);
+      uint4 t2 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 2]) + q);
+      uint4 t3 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 3]) + q);
+      acc_u8x16<KT>(key, t0, (KT)kc.mult[j]);
+      acc_u8x16<KT>(key, t1, (KT)kc.mult[j + 1]);
+      acc_u8x16<KT>(key, t2, (KT)kc.mult[j + 2]);
+      acc_u8x16<KT>(key, t3, (KT)kc.mult[j + 3]);
+    }
+    for (; j < kc.n_u8; ++j) {
+      uint4 t0 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j]) + q);
+      acc_u8x16<KT>(key, t0, (KT)kc.mult[j]);
+    }
+    for (; j < kc.K; ++j) {
+      const int4* p = reinterpret_cast<const int4*>(kc.col[j]) + q * 4;
+      int4 a0 = __ldcs(p), a1 = __ldcs(p + 1), a2 = __ldcs(p + 2), a3 = __ldcs(p + 3);
+      const KT m = (KT)kc.mult[j];
+      key[0] += (KT)(unsigned)a0.x * m; key[1] += (KT)(unsigned)a0.y * m; key[2] += (KT)(unsigned)a0.z * m; key[3] += (KT)(unsigned)a0.w * m;
+      key[4] += (KT)(unsigned)a1.x * m; key[5] += (KT)(unsigned)a1.y * m; key[6] += (KT)(unsigned)a1.z * m; key[7] += (KT)(unsigned)a1.w * m;
+      key[8] += (KT)(unsigned)a2.x * m; key[9] += (KT)(unsigned)a2.y * m; key[10] += (KT)(unsigned)a2.z * m; key[11] += (KT)(unsigned)a2.w * m;
+      key[12] += (KT)(unsigned)a3.x * m; key[13] += (KT)(unsigned)a3.y * m; key[14] += (KT)(unsigned)a3.z * m; key[15] += (KT)(unsigned)a3.w * m;
+    }
+  } else {
+    for (int e = 0; e < FR; ++e) {
+      if (base + e >= n) break;
+      KT k = 0;
+      for (int j = 0; j < kc.K; ++j) {
+        unsigned v = j < kc.n_u8 ? (unsigned)reinterpret_cast<const uint8_t*>(kc.col[j])[base + e]
+                                 : (unsigned)reinterpret_cast<const int32_t*>(kc.col[j])[base + e];
+        k += (KT)v * (KT)kc.mult[j];
+      }
+      key[e] = k;
+    }
   }
+}
+
+// sort-path fallback (key space too large for a presence table): materialise the 64-bit keys
+__global__ void __launch_bounds__(256) k_fold_keys(KeyCols kc, int64_t n, bool vec, uint64_t* __restrict__ out) {
+  const int64_t nq = ceil_div64(n, FR);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long key[FR];
+    fold_rows<unsigned long long>(kc, q, n, vec, key);
+#pragma unroll
+    for (int e = 0; e < FR; ++e)
+      if (q * FR + e < n) out[q * FR + e] = key[e];
+  }
+}
+// direct-address stage, pass 1: presence flags of the folded keys (the keys are never written out)
+__global__ void __launch_bounds__(256) k_fold_mark(KeyCols kc, int64_t n, bool vec, uint32_t* __restrict__ flags) {
+  const int64_t nq = ceil_div64(n, FR);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    unsigned key[FR];
+    fold_rows<unsigned>(kc, q, n, vec, key);
+    // test before set: with few distinct keys and many rows, unconditional stores serialise on a few L2 lines
+    // (a stale 0 from L1 only costs a redundant store; every writer stores 1)
+#pragma unroll
+    for (int e = 0; e < FR; ++e)
+      if (q * FR + e < n && flags[key[e]] == 0u) flags[key[e]] = 1u;
+  }
+}
+// pass 2: recompute the key, look up its dense sorted rank
+__global__ void __launch_bounds__(256) k_fold_lookup(KeyCols kc, int64_t n, bool vec, const uint32_t* __restrict__ rank,
+                                                     int32_t* __restrict__ gcode) {
+  const int64_t nq = ceil_div64(n, FR);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    unsigned key[FR];
+    fold_rows<unsigned>(kc, q, n, vec, key);
+    if (vec && q * FR + FR - 1 < n) {
+      int r[FR];
+#pragma unroll
+      for (int e = 0; e < FR; ++e) r[e] = (int)__ldg(rank + key[e]);
+      int4* o = reinterpret_cast<int4*>(gcode) + q * 4;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) o[a] = make_int4(r[4 * a], r[4 * a + 1], r[4 * a + 2], r[4 * a + 3]);
+    } else {
+      for (int e = 0; e < FR; ++e)
+        if (q * FR + e < n) gcode[q * FR + e] = (int)rank[key[e]];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_emit_stage_uniques(const uint32_t* __restrict__ flags,
+                                                            const uint32_t* __restrict__ rank, int64_t range,
+                                                            uint64_t* __restrict__ uniq) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range; i += (int64_t)gridDim.x * blockDim.x)
+    if (flags[i]) uniq[rank[i]] = (uint64_t)i;
 }
 
 // One decode step on the G final groups: key = uniq[code_in[g]] -> digits.  Digit 0 may be the code of the
@@ -54,30 +158,73 @@ __global__ void __launch_bounds__(256) k_unfold_keys(const uint64_t* __restrict_
   }
 }
 
-// stats[0*G + g] += w, stats[1*G + g] += w*y, stats[2*G + g] += w*y*y
+// weighted: stats[0*G + g] += w, stats[1*G + g] += w*y, stats[2*G + g] += w*y*y
+// unweighted: stats[0*G + g] += y, stats[1*G + g] += y*y   (n_g is the exact integer count of the histogram)
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(PJ_T) k_group_stats(const int32_t* __restrict__ key, const double* __restrict__ y,
                                                       const double* __restrict__ w, int64_t n,
+                                                      double* __restrict__ stats, int64_t G, bool vec_codes) {
+  constexpr int NS = WEIGHTED ? 3 : 2;
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    int k[PJ_I];
+    load4_i32(key, base, n, vec_codes, k);
+    double v[PJ_I][NS];
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e) {
+      bool valid = base + e < n;
+      double yy = valid ? __ldcs(y + base + e) : 0.0;
+      if (WEIGHTED) {
+        double ww = valid ? __ldcs(w + base + e) : 0.0;
+        v[e][0] = ww;
+        v[e][1] = ww * yy;
+        v[e][2] = ww * yy * yy;
+      } else {
+        v[e][0] = yy;
+        v[e][1] = yy * yy;
+      }
+    }
+    segmented_flush<NS>(k, v, stats, 1, 0, G);
+  }
+}
+
+// Re-aggregation of partial group tables (multi-GPU YOCO): stats[q*G + g] += part_q[i], q = n, sum_y, sum_y_sq, cnt
+__global__ void __launch_bounds__(PJ_T) k_group_merge(const int32_t* __restrict__ key, const double* __restrict__ pn,
+                                                      const double* __restrict__ psy, const double* __restrict__ psyy,
+                                                      const int32_t* __restrict__ pcnt, int64_t n,
                                                       double* __restrict__ stats, int64_t G, bool vec_codes) {
   const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
     const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
     int k[PJ_I];
     load4_i32(key, base, n, vec_codes, k);
-    double v[PJ_I][3];
+    double v[PJ_I][4];
 #pragma unroll
     for (int e = 0; e < PJ_I; ++e) {
       bool valid = base + e < n;
-      double yy = valid ? __ldcs(y + base + e) : 0.0;
-      double ww = valid ? (w ? __ldcs(w + base + e) : 1.0) : 0.0;
-      v[e][0] = ww;
-      v[e][1] = ww * yy;
-      v[e][2] = ww * yy * yy;
+      v[e][0] = valid ? pn[base + e] : 0.0;
+      v[e][1] = valid ? psy[base + e] : 0.0;
+      v[e][2] = valid ? psyy[base + e] : 0.0;
+      v[e][3] = valid ? (double)pcnt[base + e] : 0.0;   // row counts < 2^31: exact in fp64
     }
-    segmented_flush<3>(k, v, stats, 1, 0, G);
+    segmented_flush<4>(k, v, stats, 1, 0, G);
   }
+}
+__global__ void __launch_bounds__(256) k_f64_to_i32(const double* __restrict__ v, int64_t n, int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)llrint(v[i]);
 }
 
 void prim_histogram(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, uint32_t* counts, cudaStream_t s);
+void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);                  // api.cu
+void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);         // api.cu
+
+// partial tables to re-aggregate instead of raw (y, weights) rows
+struct MergeIn {
+  const double *n, *sum_y, *sum_y_sq;
+  const int32_t* cnt;
+};
 
 struct Stage {
   std::vector<int> cols;                 // original column indices folded in this stage (after the previous stage's code)
@@ -87,24 +234,31 @@ struct Stage {
   int64_t G = 0;
 };
 
-void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n_groups, int K, const double* y,
-                   const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
-                   int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
-                   cudaStream_t s) {
-  PhaseTimer t(h, s, 12);
+static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* key_dtypes, const int64_t* n_groups, int K,
+                          const double* y,
+                          const double* weights, const MergeIn* merge, int64_t n, int64_t out_cap,
+                          int32_t* const* key_codes_out, double* n_out, int32_t* cnt_out, double* sum_y_out,
+                          double* sum_y_sq_out, int64_t* n_compressed_out, cudaStream_t s) {
   LFE_REQUIRE(K >= 0 && K <= CP_MAXK, "lfe_compress: K=%d out of range [0,%d]", K, CP_MAXK);
   LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_compress: n out of range");
   if (n == 0) {
     *n_compressed_out = 0;
     return;
   }
-  for (int j = 0; j < K; ++j) LFE_REQUIRE(n_groups[j] >= 1, "lfe_compress: n_groups[%d] must be >= 1", j);
-  const int blocks = launch_blocks(h, ceil_div64(n, 1024), 8);
+  bool vec = true;   // vector loads need 4-row-aligned columns (always true for whole torch tensors)
+  for (int j = 0; j < K; ++j) {
+    LFE_REQUIRE(n_groups[j] >= 1, "lfe_compress: n_groups[%d] must be >= 1", j);
+    const int dt = key_dtypes ? key_dtypes[j] : LFE_I32;
+    LFE_REQUIRE(dt == LFE_I32 || dt == LFE_U8, "lfe_compress: key column %d: dtype must be LFE_I32 or LFE_U8", j);
+    LFE_REQUIRE(dt != LFE_U8 || n_groups[j] <= 256, "lfe_compress: uint8 key column %d needs n_groups <= 256", j);
+    vec = vec && (((uintptr_t)key_codes[j]) & (dt == LFE_U8 ? 15 : 63)) == 0;   // FR rows per aligned load group
+  }
+  const int blocks = launch_blocks(h, ceil_div64(n, 256 * FR), 8);
   const bool want_keys = key_codes_out != nullptr;
 
   // ---- staged folding -------------------------------------------------------------------------------
   std::vector<Stage> stages;
-  DevBuf<uint64_t> folded(n, s);
+  DevBuf<uint64_t> folded;   // only the sort fallback materialises the folded keys
   DevBuf<int32_t> gcode(n, s), gcode_prev;
   int64_t G = 1;
   int j = 0;
@@ -112,35 +266,77 @@ void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n
   do {
     stages.emplace_back();
     Stage& st = stages.back();
-    KeyCols kc;
-    kc.K = 0;
+    // digits of this stage in significance order: [previous stage's dense code,] then the new columns
+    std::vector<const void*> dcol;
+    std::vector<unsigned long long> dradix;
+    std::vector<bool> du8;
     unsigned long long space = 1;
     if (!first) {   // carry the previous stage's dense code as the most significant digit
       st.has_prev = true;
       st.prev_radix = (unsigned long long)G;
       std::swap(gcode, gcode_prev);
       if (!gcode.p) gcode.alloc(n, s);
-      kc.code[kc.K] = gcode_prev;
-      kc.radix[kc.K++] = (unsigned long long)G;
+      dcol.push_back(gcode_prev.p);
+      dradix.push_back((unsigned long long)G);
+      du8.push_back(false);
       space = (unsigned long long)G;
     }
     while (j < K) {
       unsigned long long r = (unsigned long long)n_groups[j];
-      bool fits = space <= CP_STAGE_SPACE / r || (kc.K == (st.has_prev ? 1 : 0));   // always take at least one column
+      bool fits = space <= CP_STAGE_SPACE / r || (dcol.size() == (st.has_prev ? 1u : 0u));   // always take at least one column
       if (!fits) break;
       LFE_REQUIRE(space <= (~0ull) / r, "lfe_compress: composite key space overflows 64 bits");
-      kc.code[kc.K] = key_codes[j];
-      kc.radix[kc.K++] = r;
+      dcol.push_back(key_codes[j]);
+      dradix.push_back(r);
+      du8.push_back(key_dtypes && key_dtypes[j] == LFE_U8);
       space *= r;
       st.cols.push_back(j++);
     }
-    k_fold_keys<<<blocks, 256, 0, s>>>(kc, n, folded);
-    KERNEL_CHECK();
-    h->n_launches += 1;
+    KeyCols kc;
+    kc.K = 0;
+    {
+      const int D = (int)dcol.size();
+      std::vector<unsigned long long> mult(D, 1ull);
+      for (int d = D - 2; d >= 0; --d) mult[d] = mult[d + 1] * dradix[d + 1];
+      for (int pass = 0; pass < 2; ++pass)            // uint8 columns first, int32 columns after
+        for (int d = 0; d < D; ++d)
+          if (du8[d] == (pass == 0)) {
+            kc.col[kc.K] = dcol[d];
+            kc.mult[kc.K++] = mult[d];
+          }
+      kc.n_u8 = 0;
+      for (int d = 0; d < D; ++d) kc.n_u8 += du8[d] ? 1 : 0;
+    }
     // distinct keys of this stage never exceed n; cap the uniques buffer by the key space
     int64_t ucap = (int64_t)((space < (unsigned long long)n) ? space : (unsigned long long)n);
     if (want_keys) st.uniq.alloc((size_t)ucap, s);   // only the decode step below needs the stage's distinct keys
-    G = factorize_dispatch(h, folded, LFE_U64, n, LFE_ORDER_SORTED, gcode, st.uniq.p, ucap, s);
+    const unsigned long long direct_limit = (unsigned long long)(16 * n > (1 << 20) ? 16 * n : (1 << 20));
+    if (space <= CP_STAGE_SPACE && space <= direct_limit) {
+      // direct-address stage: the folded key is recomputed in both passes instead of being written out
+      DevBuf<uint32_t> flags((size_t)space, s), rank((size_t)space, s), total(1, s);
+      flags.zero();
+      k_fold_mark<<<blocks, 256, 0, s>>>(kc, n, vec, flags);
+      KERNEL_CHECK();
+      prim_exclusive_scan_u32(h, flags, rank, (int64_t)space, total, s);
+      k_fold_lookup<<<blocks, 256, 0, s>>>(kc, n, vec && (((uintptr_t)gcode.p) & 63) == 0, rank, gcode);
+      KERNEL_CHECK();
+      uint32_t ht = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&ht, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      G = ht;
+      if (want_keys) {
+        k_emit_stage_uniques<<<launch_blocks(h, ceil_div64((int64_t)space, 1024), 8), 256, 0, s>>>(flags, rank, (int64_t)space,
+                                                                                                    st.uniq);
+        KERNEL_CHECK();
+      }
+      h->n_launches += 3;
+    } else {
+      if (!folded.p) folded.alloc(n, s);
+      k_fold_keys<<<blocks, 256, 0, s>>>(kc, n, vec, folded);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      G = factorize_dispatch(h, folded, LFE_U64, n, LFE_ORDER_SORTED, gcode, st.uniq.p, ucap, s);
+    }
     st.G = G;
     first = false;
   } while (j < K);
@@ -174,17 +370,117 @@ void compress_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n
       code_out = (code_out == ca.p) ? cb.p : ca.p;
     }
   }
-  if (cnt_out) prim_histogram(h, gcode, n, G, (uint32_t*)cnt_out, s);
-  if (y && n_out && sum_y_out && sum_y_sq_out) {
-    DevBuf<double> stats((size_t)3 * G, s);
+  if (merge) {
+    DevBuf<double> stats((size_t)4 * G, s);
     stats.zero();
     int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
-    k_group_stats<<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, weights, n, stats, G,
-                                                                 (((uintptr_t)gcode.p) & 15) == 0);
+    k_group_merge<<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, merge->n, merge->sum_y, merge->sum_y_sq, merge->cnt,
+                                                                 n, stats, G, (((uintptr_t)gcode.p) & 15) == 0);
     KERNEL_CHECK();
-    h->n_launches += 1;
     CUDA_CHECK(cudaMemcpyAsync(n_out, stats.p, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(sum_y_out, stats.p + G, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(sum_y_sq_out, stats.p + 2 * G, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (cnt_out) {
+      k_f64_to_i32<<<launch_blocks(h, ceil_div64(G, 256), 8), 256, 0, s>>>(stats.p + 3 * G, G, cnt_out);
+      KERNEL_CHECK();
+    }
+    h->n_launches += 2;
+    return;
   }
+  const bool want_stats = y && n_out && sum_y_out && sum_y_sq_out;
+  DevBuf<uint32_t> cnt_tmp;
+  uint32_t* cnt = (uint32_t*)cnt_out;
+  if (!cnt && want_stats && !weights) {
+    cnt_tmp.alloc((size_t)G, s);
+    cnt = cnt_tmp.p;
+  }
+  if (cnt) prim_histogram(h, gcode, n, G, cnt, s);
+  if (want_stats) {
+    const int NS = weights ? 3 : 2;
+    DevBuf<double> stats((size_t)NS * G, s);
+    stats.zero();
+    int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+    const bool vc = (((uintptr_t)gcode.p) & 15) == 0;
+    if (weights) k_group_stats<true><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, weights, n, stats, G, vc);
+    else k_group_stats<false><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, nullptr, n, stats, G, vc);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    const double* sy = stats.p + (weights ? G : 0);
+    if (weights) CUDA_CHECK(cudaMemcpyAsync(n_out, stats.p, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    else prim_u32_to_f64(h, cnt, G, n_out, s);   // unweighted: _n is the exact integer group size
+    CUDA_CHECK(cudaMemcpyAsync(sum_y_out, sy, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(sum_y_sq_out, sy + G, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+}
+
+void compress_impl(lfe_ctx* h, const void* const* key_codes, const int* key_dtypes, const int64_t* n_groups, int K,
+                   const double* y, const double* weights, int64_t n, int64_t out_cap, int32_t* const* key_codes_out,
+                   double* n_out, int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
+                   cudaStream_t s) {
+  PhaseTimer t(h, s, 12);
+  compress_core(h, key_codes, key_dtypes, n_groups, K, y, weights, nullptr, n, out_cap, key_codes_out, n_out, cnt_out, sum_y_out,
+                sum_y_sq_out, n_compressed_out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU YOCO: every rank compresses its own rows (no data-path collective over the N rows), then the
+// partial group tables -- G_r rows each, tiny next to N -- are all-gathered and re-aggregated, so every
+// rank ends up with the identical global table.  The gather is a sum all-reduce over a zero-initialised
+// buffer in which each rank fills its own slice (codes and counts as uint32, statistics as fp64).
+// Without a communicator this merges duplicate keys inside the one table it is given.
+// ---------------------------------------------------------------------------------------------
+void compress_merge_impl(lfe_ctx* h, const int32_t* const* key_codes, const int64_t* n_groups, int K,
+                         const double* n_in, const int32_t* cnt_in, const double* sum_y_in, const double* sum_y_sq_in,
+                         int64_t n_rows, int64_t out_cap, int32_t* const* key_codes_out, double* n_out,
+                         int32_t* cnt_out, double* sum_y_out, double* sum_y_sq_out, int64_t* n_compressed_out,
+                         cudaStream_t s) {
+  PhaseTimer t(h, s, 12);
+  LFE_REQUIRE(K >= 1 && K <= CP_MAXK, "lfe_compress_merge: K=%d out of range [1,%d]", K, CP_MAXK);
+  LFE_REQUIRE(n_rows >= 0 && n_in && cnt_in && sum_y_in && sum_y_sq_in && n_out && sum_y_out && sum_y_sq_out &&
+                  key_codes_out, "lfe_compress_merge: NULL argument");
+  if (h->world <= 1) {
+    MergeIn m{n_in, sum_y_in, sum_y_sq_in, cnt_in};
+    compress_core(h, (const void* const*)key_codes, nullptr, n_groups, K, nullptr, nullptr, &m, n_rows, out_cap, key_codes_out, n_out, cnt_out,
+                  sum_y_out, sum_y_sq_out, n_compressed_out, s);
+    return;
+  }
+  const int W = h->world;
+  DevBuf<double> sizes(W, s);
+  sizes.zero();
+  const double mine = (double)n_rows;
+  CUDA_CHECK(cudaMemcpyAsync(sizes.p + h->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+  comm_allreduce(h, sizes.p, W, 0, s);
+  std::vector<double> hs(W);
+  CUDA_CHECK(cudaMemcpyAsync(hs.data(), sizes.p, W * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  int64_t total = 0, off = 0;
+  for (int r = 0; r < W; ++r) {
+    if (r == h->rank) off = total;
+    total += (int64_t)hs[r];
+  }
+  LFE_REQUIRE(total < (int64_t)0x7fffffff, "lfe_compress_merge: gathered table too large");
+  if (total == 0) {
+    *n_compressed_out = 0;
+    return;
+  }
+  DevBuf<uint32_t> gi((size_t)(K + 1) * total, s);   // K code columns + raw counts
+  DevBuf<double> gd((size_t)3 * total, s);           // n, sum_y, sum_y_sq
+  gi.zero();
+  gd.zero();
+  if (n_rows > 0) {
+    for (int j = 0; j < K; ++j)
+      CUDA_CHECK(cudaMemcpyAsync(gi.p + (size_t)j * total + off, key_codes[j], n_rows * sizeof(int32_t),
+                                 cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(gi.p + (size_t)K * total + off, cnt_in, n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(gd.p + off, n_in, n_rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(gd.p + total + off, sum_y_in, n_rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(gd.p + 2 * total + off, sum_y_sq_in, n_rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  comm_allreduce_int(h, gi.p, (int64_t)(K + 1) * total, 0, 0, s);
+  comm_allreduce(h, gd.p, 3 * total, 0, s);
+  std::vector<const void*> kc(K);
+  for (int j = 0; j < K; ++j) kc[j] = gi.p + (size_t)j * total;
+  MergeIn m{gd.p, gd.p + total, gd.p + 2 * total, (const int32_t*)(gi.p + (size_t)K * total)};
+  compress_core(h, kc.data(), nullptr, n_groups, K, nullptr, nullptr, &m, total, out_cap, key_codes_out, n_out, cnt_out,
+                sum_y_out, sum_y_sq_out, n_compressed_out, s);
 }

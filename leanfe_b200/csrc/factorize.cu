@@ -6,6 +6,7 @@
 // case for panel ids) a direct-address presence table + scan gives the ranks in three streaming
 // passes; otherwise a stable LSD radix argsort of (key - min) does.
 #include <climits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -87,8 +88,12 @@ __global__ void __launch_bounds__(256) k_minmax(const typename KeyIO<DT>::T* __r
 template <int DT>
 __global__ void __launch_bounds__(256) k_mark(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
                                               unsigned long long kmin, uint32_t* __restrict__ flags) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    flags[KeyIO<DT>::enc(keys[i]) - kmin] = 1u;  // benign race: every writer stores 1
+  // test before set: low-cardinality keys would otherwise serialise millions of stores on a few L2 lines
+  // (a stale 0 from L1 only costs a redundant store; every writer stores 1)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t* f = flags + (KeyIO<DT>::enc(keys[i]) - kmin);
+    if (*f == 0u) *f = 1u;
+  }
 }
 
 template <int DT>
@@ -265,7 +270,7 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
 // ---- float keys that are really small integers (dummies, counts, years stored as double) -------------
 // flags[0] |= 1 if any value is non-integral / non-finite / outside +-2^52 ; mm = {min, max} as int64
 __global__ void __launch_bounds__(256) k_f64_integral_range(const double* __restrict__ v, int64_t n,
-                                                            int* __restrict__ bad, long long* __restrict__ mm) {
+                                                            unsigned int* __restrict__ bad, long long* __restrict__ mm) {
   long long lo = LLONG_MAX, hi = LLONG_MIN;
   int b = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(256) k_f64_integral_range(const double* __rest
     b |= __shfl_xor_sync(0xffffffffu, b, d);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (b) atomicOr(bad, 1);
+    if (b) atomicOr(bad, 1u);
     atomicMin(&mm[0], lo);
     atomicMax(&mm[1], hi);
   }
@@ -300,25 +305,40 @@ __global__ void __launch_bounds__(256) k_i64_to_f64(const long long* __restrict_
 // Integer-valued doubles with a small range take the direct-address path instead of a 64-bit radix sort.
 static bool factorize_f64_as_int(lfe_ctx* h, const double* keys, int64_t n, int order, int32_t* codes, double* uniques,
                                  int64_t uniques_cap, cudaStream_t s, int64_t* G_out) {
-  if (n <= 0 || (order & LFE_ORDER_GLOBAL)) return false;
-  DevBuf<int> bad(1, s);
+  // With a shared code space (LFE_ORDER_GLOBAL) the decision is taken on all-reduced quantities, so every
+  // rank follows the same branch and issues the same collectives -- also a rank that holds no rows.
+  const bool global = (order & LFE_ORDER_GLOBAL) != 0 && h->world > 1;
+  if (n <= 0 && !global) return false;
+  DevBuf<unsigned int> bad(1, s);
   DevBuf<long long> mm(2, s);
   bad.zero();
   long long init[2] = {LLONG_MAX, LLONG_MIN};
   CUDA_CHECK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-  int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
-  k_f64_integral_range<<<blocks, 256, 0, s>>>(keys, n, bad, mm);
-  KERNEL_CHECK();
-  int hb = 0;
+  int blocks = launch_blocks(h, ceil_div64(n > 0 ? n : 1, 256 * 4), 8);
+  if (n > 0) {
+    k_f64_integral_range<<<blocks, 256, 0, s>>>(keys, n, bad, mm);
+    KERNEL_CHECK();
+  }
+  if (global) {
+    comm_allreduce_int(h, bad.p, 1, 0, 2, s);
+    comm_allreduce_int(h, mm.p, 1, 2, 3, s);
+    comm_allreduce_int(h, mm.p + 1, 1, 2, 2, s);
+  }
+  unsigned int hb = 0;
   long long hmm[2];
-  CUDA_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   h->n_launches += 1;
-  if (hb || hmm[1] < hmm[0] || (unsigned long long)(hmm[1] - hmm[0]) >= (1ull << 24)) return false;
-  DevBuf<long long> ik(n, s), iu;
-  k_f64_to_i64<<<blocks, 256, 0, s>>>(keys, n, ik);
-  KERNEL_CHECK();
+  if (hb || hmm[1] < hmm[0] || (unsigned long long)(hmm[1] - hmm[0]) >= (1ull << 24)) {
+    LFE_REQUIRE(!global, "lfe_factorize: LFE_ORDER_GLOBAL on float keys needs integer-valued data with a range < 2^24");
+    return false;
+  }
+  DevBuf<long long> ik(n > 0 ? n : 1, s), iu;
+  if (n > 0) {
+    k_f64_to_i64<<<blocks, 256, 0, s>>>(keys, n, ik);
+    KERNEL_CHECK();
+  }
   if (uniques) iu.alloc((size_t)(hmm[1] - hmm[0] + 1), s);
   int64_t G = factorize_impl<LFE_I64>(h, ik.p, n, order, codes, uniques ? iu.p : nullptr, hmm[1] - hmm[0] + 1, s);
   if (uniques && G <= uniques_cap) {
@@ -345,6 +365,89 @@ int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t 
     case LFE_F64: return factorize_impl<LFE_F64>(h, keys, n, order, codes, uniques, uniques_cap, s);
     case LFE_U8: return factorize_impl<LFE_U8>(h, keys, n, order, codes, uniques, uniques_cap, s);
     default: LFE_THROW(LFE_ERR_ARG, "lfe_factorize: unknown key dtype %d", key_dtype);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// [min, max] of K integer key columns in one call (one sync): lets the caller use small raw values
+// (uint8 dummies) directly as group codes, radix = max + 1, instead of factorising every column.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename V, int W>   // V = 16-byte vector of W elements of T
+__global__ void __launch_bounds__(256) k_range(const T* __restrict__ v, int64_t n, bool vec, long long* __restrict__ mm) {
+  long long lo = LLONG_MAX, hi = LLONG_MIN;
+  const int64_t nv = vec ? n / W : 0;
+#pragma unroll 4
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (int64_t)gridDim.x * blockDim.x) {
+    V t = __ldcs(reinterpret_cast<const V*>(v) + q);
+    const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      long long x = (long long)e[i];
+      lo = x < lo ? x : lo;
+      hi = x > hi ? x : hi;
+    }
+  }
+  for (int64_t i = nv * W + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    long long x = (long long)v[i];
+    lo = x < lo ? x : lo;
+    hi = x > hi ? x : hi;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    long long a = __shfl_xor_sync(0xffffffffu, lo, d), c = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo;
+    hi = c > hi ? c : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
+void key_ranges_impl(lfe_ctx* h, const void* const* cols, const int* dtypes, int K, int64_t n, int64_t* min_out,
+                     int64_t* max_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 0);
+  LFE_REQUIRE(K >= 1 && K <= 1024, "lfe_key_ranges: K out of range");
+  std::vector<long long> init(2 * K);
+  for (int j = 0; j < K; ++j) {
+    init[2 * j] = LLONG_MAX;
+    init[2 * j + 1] = LLONG_MIN;
+  }
+  DevBuf<long long> mm(2 * K, s);
+  CUDA_CHECK(cudaMemcpyAsync(mm.p, init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));   // init is a host stack/heap buffer
+  const int blocks = launch_blocks(h, ceil_div64(n > 0 ? n : 1, 256 * 16), 8);
+  for (int j = 0; j < K && n > 0; ++j) {
+    const bool vec = (((uintptr_t)cols[j]) & 15) == 0;
+    switch (dtypes[j]) {
+      case LFE_U8: k_range<uint8_t, uint4, 16><<<blocks, 256, 0, s>>>((const uint8_t*)cols[j], n, vec, mm.p + 2 * j); break;
+      case LFE_I32: k_range<int32_t, int4, 4><<<blocks, 256, 0, s>>>((const int32_t*)cols[j], n, vec, mm.p + 2 * j); break;
+      case LFE_I64: k_range<long long, longlong2, 2><<<blocks, 256, 0, s>>>((const long long*)cols[j], n, vec, mm.p + 2 * j); break;
+      default: LFE_THROW(LFE_ERR_ARG, "lfe_key_ranges: column %d: dtype must be LFE_U8, LFE_I32 or LFE_I64", j);
+    }
+    KERNEL_CHECK();
+  }
+  h->n_launches += K;
+  if (h->world > 1) {   // the ranges of the whole (sharded) column; interleaved {min, max} pairs -> two strided passes
+    std::vector<long long> tmp(2 * K);
+    DevBuf<long long> lo(K, s), hi(K, s);
+    CUDA_CHECK(cudaMemcpy2DAsync(lo.p, sizeof(long long), mm.p, 2 * sizeof(long long), sizeof(long long), K,
+                                 cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpy2DAsync(hi.p, sizeof(long long), mm.p + 1, 2 * sizeof(long long), sizeof(long long), K,
+                                 cudaMemcpyDeviceToDevice, s));
+    comm_allreduce_int(h, lo.p, K, 2, 3, s);
+    comm_allreduce_int(h, hi.p, K, 2, 2, s);
+    CUDA_CHECK(cudaMemcpyAsync(min_out, lo.p, K * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(max_out, hi.p, K * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return;
+  }
+  std::vector<long long> host(2 * K);
+  CUDA_CHECK(cudaMemcpyAsync(host.data(), mm.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int j = 0; j < K; ++j) {
+    min_out[j] = host[2 * j];
+    max_out[j] = host[2 * j + 1];
   }
 }
 

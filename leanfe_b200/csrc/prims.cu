@@ -170,11 +170,43 @@ __global__ void __launch_bounds__(256) k_hist_global(const int32_t* __restrict__
   }
 }
 
+// Mid-size histograms (8k < G <= 48k bins, e.g. the 24 000 YOCO groups of BASELINE config 4): one 1024-thread
+// CTA per SM privatises all bins in up to 192 KB of shared memory; 128-bit code loads, native shared atomics.
+constexpr int HG_BIG_BINS = 48 * 1024;
+__global__ void __launch_bounds__(1024, 1) k_hist_smem_big(const int32_t* __restrict__ codes, int64_t n, int G,
+                                                           uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sh[];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const int64_t nv = n / 4;
+  const int4* cv = reinterpret_cast<const int4*>(codes);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldcs(cv + q);
+    atomicAdd(&sh[c.x], 1u);
+    atomicAdd(&sh[c.y], 1u);
+    atomicAdd(&sh[c.z], 1u);
+    atomicAdd(&sh[c.w], 1u);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sh[codes[i]], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x)
+    if (sh[i]) atomicAdd(&counts[i], sh[i]);
+}
+
 void prim_histogram(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, uint32_t* counts, cudaStream_t s) {
   CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)G * sizeof(uint32_t), s));
   if (n <= 0) return;
   int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 8);
-  if (G <= HG_SMEM_BINS) {
+  if (G > HG_SMEM_BINS && G <= HG_BIG_BINS && n >= 256 * G && (((uintptr_t)codes) & 15) == 0 &&
+      (size_t)G * sizeof(uint32_t) <= (size_t)h->smem_optin) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_hist_smem_big, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_BIG_BINS * 4));
+      attr_set = true;
+    }
+    k_hist_smem_big<<<h->sm_count, 1024, (size_t)G * sizeof(uint32_t), s>>>(codes, n, (int)G, counts);
+  } else if (G <= HG_SMEM_BINS) {
     k_hist_smem<<<blocks, 256, (size_t)G * sizeof(uint32_t), s>>>(codes, n, (int)G, counts);
   } else {
     k_hist_global<<<blocks, 256, 0, s>>>(codes, n, counts);

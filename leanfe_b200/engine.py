@@ -109,10 +109,12 @@ class Engine:
         cap = 0
         if want_uniques:
             cap = n if uniques_cap is None else min(n, int(uniques_cap))
+            if order & capi.ORDER_GLOBAL and self.world > 1:
+                cap = int(uniques_cap or (1 << 20))     # the shared code space may hold keys this rank never sees
             uniq = self.empty(cap, keys.dtype)
         rc = self.lib.lfe_factorize(self.h, self._p(keys), _TORCH_TO_LFE[keys.dtype], n, order, self._p(codes),
                                     C.byref(G), self._p(uniq), cap, self.stream)
-        if rc == capi.ERR_CAPACITY and want_uniques and cap < n:
+        if rc == capi.ERR_CAPACITY and want_uniques and cap < n and not (order & capi.ORDER_GLOBAL and self.world > 1):
             return self.factorize(keys, order, True, n)
         capi.check(rc)
         return codes, int(G.value), (uniq[: G.value] if uniq is not None else None)
@@ -268,13 +270,18 @@ class Engine:
     # -- (3) compress -------------------------------------------------------------------------
     def compress(self, key_codes: list[torch.Tensor], n_groups: list[int], y: torch.Tensor | None,
                  weights: torch.Tensor | None = None, out_cap: int | None = None, count_only: bool = False):
-        """-> dict(n_compressed, key_codes, n, cnt, sum_y, sum_y_sq)"""
+        """-> dict(n_compressed, key_codes, n, cnt, sum_y, sum_y_sq).  Key columns are int32 codes, or uint8
+        raw values used as codes (n_groups = max + 1)."""
         self._check_dev(*key_codes, y, weights)
         n = key_codes[0].numel() if key_codes else (y.numel() if y is not None else 0)
         K = len(key_codes)
+        for t in key_codes:
+            if t.dtype not in (torch.int32, torch.uint8) or t.numel() != n or not t.is_contiguous():
+                raise TypeError("compress: key columns must be contiguous int32 codes or uint8 values of equal length")
+        dts = capi.i32_array([capi.LFE_U8 if t.dtype == torch.uint8 else capi.LFE_I32 for t in key_codes])
         G = C.c_int64(0)
         if count_only:
-            capi.check(self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]),
+            capi.check(self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]), dts,
                                              capi.i64_array(n_groups), K, None, None, n, 0, None, None, None, None,
                                              None, C.byref(G), self.stream))
             return dict(n_compressed=int(G.value))
@@ -286,7 +293,7 @@ class Engine:
             kout = [self.empty(cap, torch.int32) for _ in range(K)]
             nn, sy, syy = (self.empty(cap, torch.float64) for _ in range(3))
             cnt = self.empty(cap, torch.int32)
-            rc = self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]),
+            rc = self.lib.lfe_compress(self.h, capi.ptr_array([t.data_ptr() for t in key_codes]), dts,
                                        capi.i64_array(n_groups), K, self._p(y), self._p(weights), n, cap,
                                        capi.ptr_array([t.data_ptr() for t in kout]), self._p(nn), self._p(cnt),
                                        self._p(sy), self._p(syy), C.byref(G), self.stream)
@@ -318,6 +325,63 @@ class Engine:
     def allreduce(self, t: torch.Tensor):
         capi.check(self.lib.lfe_allreduce_f64(self.h, self._p(t), t.numel(), self.stream))
         return t
+
+    def key_ranges(self, cols: list[torch.Tensor]):
+        """lfe_key_ranges: -> [(min, max)] of integer columns (uint8 / int32 / int64), one pass each, one sync;
+        with a communicator attached, of the whole sharded columns."""
+        self._check_dev(*cols)
+        K, n = len(cols), cols[0].numel()
+        lo, hi = (C.c_int64 * K)(), (C.c_int64 * K)()
+        capi.check(self.lib.lfe_key_ranges(self.h, capi.ptr_array([t.data_ptr() for t in cols]),
+                                           capi.i32_array([_TORCH_TO_LFE[t.dtype] for t in cols]), K, n, lo, hi,
+                                           self.stream))
+        return [(int(a), int(b)) for a, b in zip(lo, hi)]
+
+    def compress_merge(self, part: dict, n_groups: list[int]):
+        """lfe_compress_merge: all-gather + re-aggregate the ranks' partial YOCO tables (the dicts returned by
+        :meth:`compress`); every rank gets the identical global table.  -> dict like :meth:`compress`"""
+        keys = part["key_codes"]
+        K, rows = len(keys), int(part["n_compressed"])
+        self._check_dev(*keys, part["n"], part["cnt"], part["sum_y"], part["sum_y_sq"])
+        space = 1
+        for g in n_groups:
+            space *= int(g)
+        tot = self.empty(1, torch.float64)
+        tot.fill_(float(rows))
+        cap = int(min(space, int(self.allreduce(tot).item()))) if self.world > 1 else rows
+        cap = max(cap, 1)
+        kout = [self.empty(cap, torch.int32) for _ in range(K)]
+        nn, sy, syy = (self.empty(cap, torch.float64) for _ in range(3))
+        cnt = self.empty(cap, torch.int32)
+        G = C.c_int64(0)
+        capi.check(self.lib.lfe_compress_merge(
+            self.h, capi.ptr_array([t.data_ptr() for t in keys]), capi.i64_array(n_groups), K, self._p(part["n"]),
+            self._p(part["cnt"]), self._p(part["sum_y"]), self._p(part["sum_y_sq"]), rows, cap,
+            capi.ptr_array([t.data_ptr() for t in kout]), self._p(nn), self._p(cnt), self._p(sy), self._p(syy),
+            C.byref(G), self.stream))
+        g = int(G.value)
+        return dict(n_compressed=g, key_codes=[t[:g] for t in kout], n=nn[:g], cnt=cnt[:g], sum_y=sy[:g],
+                    sum_y_sq=syy[:g])
+
+    def replicated(self):
+        """Context manager: the calls inside run rank-locally although a communicator is attached (work that
+        every rank repeats on identical data, e.g. the solve on the merged YOCO table)."""
+        return _Replicated(self)
+
+
+class _Replicated:
+    def __init__(self, eng):
+        self.eng = eng
+
+    def __enter__(self):
+        capi.check(self.eng.lib.lfe_comm_set_active(self.eng.h, 0))
+        self.saved, self.eng.world = self.eng.world, 1
+        return self.eng
+
+    def __exit__(self, *exc):
+        self.eng.world = self.saved
+        capi.check(self.eng.lib.lfe_comm_set_active(self.eng.h, 1))
+        return False
 
 
 class DemeanPlan:

@@ -87,6 +87,40 @@ def main():
         if not ok:
             failures.append(("3way", vc, cl, wname, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs,
                              ref["n_obs"], res.fe_dims, ref["fe_dims"]))
+    # YOCO (strategy='compress'): rows sharded ARBITRARILY (round-robin), every key spans ranks; one dummy is
+    # non-zero on rank 0's rows only, one period exists on rank 1's rows only (shared code space needed)
+    Ny, ng, npd = 400_000, 150, 10
+    grp, per = rng.integers(0, ng, Ny), rng.integers(0, npd - 1, Ny)
+    per[(np.arange(Ny) % world == min(1, world - 1)) & (rng.random(Ny) < 0.02)] = npd - 1
+    treated = (grp % 5 < 2)
+    d1 = (treated & (per >= 5)).astype(np.uint8)
+    d2 = (treated & (per == 7)).astype(np.uint8)
+    d3 = ((np.arange(Ny) % world == 0) & (rng.random(Ny) < 0.1)).astype(np.uint8)
+    dose = rng.integers(0, 4, Ny).astype(np.float64)          # integer-valued float regressor
+    wy = rng.integers(1, 4, Ny).astype(np.float64)
+    yz = 0.8 * d1 - 0.3 * d2 + 0.2 * d3 + 0.1 * dose + rng.normal(size=ng)[grp] + 0.05 * per + rng.normal(size=Ny)
+    fully = dict(y=yz, d1=d1, d2=d2, d3=d3, dose=dose, grp=grp, per=per, wy=wy)
+    mine_y = np.arange(rank, Ny, world)
+    shardy = {k: v[mine_y] for k, v in fully.items()}
+    for vc, cl, wname in (("iid", None, None), ("hc1", None, None), ("cluster", ["grp"], None),
+                          ("cluster", ["grp", "per"], None), ("iid", None, "wy")):
+        kw = dict(formula="y ~ d1 + d2 + d3 + dose | grp + per", vcov=vc, cluster_cols=cl, weights=wname,
+                  strategy="compress")
+        res = leanfe(shardy, **kw)
+        ref = O.leanfe_oracle(fully, **kw)
+        b, eb = np.array(list(res.coefs.values())), np.array(list(ref["coefs"].values()))
+        s, es = np.array(list(res.std_errors.values())), np.array(list(ref["std_errors"].values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and res.n_compressed == ref["n_compressed"] and res.n_clusters == ref["n_clusters"])
+        t = torch.tensor(list(b) + list(s), dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and bool(torch.equal(lo, hi))
+        if not ok:
+            failures.append(("yoco", vc, cl, wname, b, eb, s, es, res.n_obs, ref["n_obs"], res.df_resid, ref["df_resid"],
+                             res.n_compressed, ref["n_compressed"], res.n_clusters, ref["n_clusters"]))
     if rank == 0:
         print("multigpu_check:", "OK" if not failures else f"FAILED {failures}", f"(world={world})")
     dist.destroy_process_group()

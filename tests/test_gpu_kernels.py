@@ -341,6 +341,76 @@ def test_compress_known_answer_from_reference_docstring(eng):
     np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), [5.0, 9.0])
 
 
+@pytest.mark.parametrize("n", [5, 4099, 250_001])
+def test_compress_raw_uint8_keys_match_factorized_keys(eng, n):
+    """uint8 key columns grouped on their raw values (no dictionary pass) give the same groups, counts and
+    sums as the same columns factorised first; key_ranges supplies the radix."""
+    rng = np.random.default_rng(n)
+    d = [rng.integers(0, 2, n).astype(np.uint8) for _ in range(12)]
+    d.append((rng.integers(0, 3, n) * 2).astype(np.uint8))            # values {0, 2, 4}: a gap in the raw code space
+    ids = rng.integers(0, 37, n)
+    y = rng.normal(size=n)
+    d_dev = [dev(c) for c in d]
+    rng_ = eng.key_ranges(d_dev + [dev(ids), dev(ids.astype(np.int32) - 5)])
+    assert rng_ == [(int(c.min()), int(c.max())) for c in d] + [(int(ids.min()), int(ids.max())),
+                                                                  (int(ids.min()) - 5, int(ids.max()) - 5)]
+    ic, iG, _ = eng.factorize(dev(ids))
+    raw = eng.compress(d_dev + [ic], [hi + 1 for _, hi in rng_[:13]] + [iG], dev(y))
+    fk, fG, fu = [], [], []
+    for c in d_dev:
+        cc, G, u = eng.factorize(c, want_uniques=True)
+        fk.append(cc); fG.append(G); fu.append(u)
+    ref = eng.compress(fk + [ic], fG + [iG], dev(y))
+    exp = O.compress(y, d + [ids], None)
+    assert raw["n_compressed"] == ref["n_compressed"] == exp["n_compressed"]
+    assert torch.equal(raw["cnt"], ref["cnt"])
+    for j in range(13):                                                 # raw key out = the value itself
+        assert torch.equal(raw["key_codes"][j].long(), fu[j].long()[ref["key_codes"][j].long()])
+    assert torch.equal(raw["key_codes"][13], ref["key_codes"][13])
+    np.testing.assert_array_equal(raw["cnt"].cpu().numpy(), exp["n"].astype(np.int64))
+    np.testing.assert_allclose(raw["sum_y"].cpu().numpy(), exp["sum_y"], rtol=1e-10, atol=1e-10)
+    # misaligned views take the scalar path
+    off = eng.compress([c[1:] for c in d_dev] + [ic[1:].contiguous()], [hi + 1 for _, hi in rng_[:13]] + [iG], dev(y[1:]))
+    exp1 = O.compress(y[1:], [c[1:] for c in d] + [ids[1:]], None)
+    assert off["n_compressed"] == exp1["n_compressed"]
+    np.testing.assert_array_equal(off["cnt"].cpu().numpy(), exp1["n"].astype(np.int64))
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_compress_merge_of_partial_tables_equals_whole(eng, weighted):
+    """lfe_compress_merge (multi-GPU YOCO, here on one device): group-by of the concatenated per-shard tables
+    == group-by of all rows; keys and counts bit-exact, sums to rounding."""
+    rng = np.random.default_rng(33)
+    n = 200_000
+    keys = [rng.integers(0, 2, n), rng.integers(0, 40, n), rng.integers(0, 9, n)]
+    keys[0][: n // 3] = 0                                   # a key value absent from the first shard
+    y = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    kc, Gs = [], []
+    for kcol in keys:
+        c, G, _ = eng.factorize(dev(kcol))
+        kc.append(c)
+        Gs.append(G)
+    whole = eng.compress(kc, Gs, dev(y), dev(w) if weighted else None)
+    cuts = [0, n // 3, n // 3 + 17, n]                      # ragged shards, one tiny
+    parts = [eng.compress([c[a:b_].contiguous() for c in kc], Gs, dev(y[a:b_]), dev(w[a:b_]) if weighted else None)
+             for a, b_ in zip(cuts[:-1], cuts[1:])]
+    cat = dict(n_compressed=sum(p["n_compressed"] for p in parts),
+               key_codes=[torch.cat([p["key_codes"][j] for p in parts]) for j in range(len(kc))],
+               **{f: torch.cat([p[f] for p in parts]) for f in ("n", "cnt", "sum_y", "sum_y_sq")})
+    got = eng.compress_merge(cat, Gs)
+    assert got["n_compressed"] == whole["n_compressed"]
+    for a, b_ in zip(got["key_codes"], whole["key_codes"]):
+        assert torch.equal(a, b_)
+    assert torch.equal(got["cnt"], whole["cnt"])
+    for f in ("n", "sum_y", "sum_y_sq"):
+        np.testing.assert_allclose(got[f].cpu().numpy(), whole[f].cpu().numpy(), rtol=1e-12, atol=1e-11)
+    again = eng.compress_merge(got, Gs)                     # idempotent on a table without duplicate keys
+    assert again["n_compressed"] == got["n_compressed"] and torch.equal(again["cnt"], got["cnt"])
+    with eng.replicated() as e2:                            # no communicator attached: a no-op scope
+        assert e2.world == 1
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: tiny / ragged inputs, plan reuse, many columns, every row its own group
 # ------------------------------------------------------------------------------------------------
