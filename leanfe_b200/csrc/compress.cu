@@ -32,104 +32,126 @@ struct KeyCols {
   int n_u8, K;
 };
 
-constexpr int FR = 16;   // consecutive rows per thread: one 128-bit load per uint8 column, four per int32 column
+constexpr int FR = 16;          // rows per thread
+constexpr int FW = 32 * FR;     // rows per warp tile
 
-// Folded keys of FR consecutive rows (q = row / FR).  KT = unsigned (direct-address stages, key space <= 2^26)
-// or unsigned long long.  Loads are issued four columns at a time before they are consumed, so every thread
-// keeps 64 bytes in flight.
+// Folded keys of one warp tile of FW consecutive rows.  Lane l owns rows 128 e + 4 l + i (e, i = 0..3; key index
+// 4 e + i), so that every load and store of the warp is one fully coalesced request: four 32-bit loads per lane
+// from a uint8 column (128 B per warp each), four 128-bit loads from an int32 column (512 B per warp each).
+// KT = unsigned (direct-address stages, key space <= 2^26) or unsigned long long.  The loads of four uint8
+// columns are issued before they are consumed.
 template <typename KT>
-__device__ __forceinline__ void acc_u8x16(KT key[FR], const uint4& t, KT m) {
-  const unsigned w[4] = {t.x, t.y, t.z, t.w};
+__device__ __forceinline__ void acc_u8(KT key[FR], const unsigned w[4], KT m) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) key[4 * a + b] += (KT)((w[a] >> (8 * b)) & 0xffu) * m;
+    for (int i = 0; i < 4; ++i) key[4 * e + i] += (KT)((w[e] >> (8 * i)) & 0xffu) * m;
+}
+__device__ __forceinline__ void ld_u8(const void* col, int64_t base, int lane, unsigned w[4]) {
+  const unsigned* p = reinterpret_cast<const unsigned*>(col) + base / 4 + lane;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = __ldcs(p + 32 * e);
 }
 template <typename KT>
-__device__ __forceinline__ void fold_rows(const KeyCols& kc, int64_t q, int64_t n, bool vec, KT key[FR]) {
-  const int64_t base = q * FR;
+__device__ __forceinline__ void fold_tile(const KeyCols& kc, int64_t base, int64_t n, bool vec, int lane, KT key[FR]) {
 #pragma unroll
   for (int e = 0; e < FR; ++e) key[e] = 0;
-  if (vec && base + FR - 1 < n) {
+  if (vec && base + FW <= n) {
     int j = 0;
     for (; j + 4 <= kc.n_u8; j += 4) {
-      uint4 t0 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j]) + q);
-      uint4 t1 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 1]) + q);
-      uint4 t2 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 2]) + q);
-      uint4 t3 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j + 3]) + q);
-      acc_u8x16<KT>(key, t0, (KT)kc.mult[j]);
-      acc_u8x16<KT>(key, t1, (KT)kc.mult[j + 1]);
-      acc_u8x16<KT>(key, t2, (KT)kc.mult[j + 2]);
-      acc_u8x16<KT>(key, t3, (KT)kc.mult[j + 3]);
+      unsigned w0[4], w1[4], w2[4], w3[4];
+      ld_u8(kc.col[j], base, lane, w0);
+      ld_u8(kc.col[j + 1], base, lane, w1);
+      ld_u8(kc.col[j + 2], base, lane, w2);
+      ld_u8(kc.col[j + 3], base, lane, w3);
+      acc_u8<KT>(key, w0, (KT)kc.mult[j]);
+      acc_u8<KT>(key, w1, (KT)kc.mult[j + 1]);
+      acc_u8<KT>(key, w2, (KT)kc.mult[j + 2]);
+      acc_u8<KT>(key, w3, (KT)kc.mult[j + 3]);
     }
     for (; j < kc.n_u8; ++j) {
-      uint4 t0 = __ldcs(reinterpret_cast<const uint4*>(kc.col[j]) + q);
-      acc_u8x16<KT>(key, t0, (KT)kc.mult[j]);
+      unsigned w0[4];
+      ld_u8(kc.col[j], base, lane, w0);
+      acc_u8<KT>(key, w0, (KT)kc.mult[j]);
     }
     for (; j < kc.K; ++j) {
-      const int4* p = reinterpret_cast<const int4*>(kc.col[j]) + q * 4;
-      int4 a0 = __ldcs(p), a1 = __ldcs(p + 1), a2 = __ldcs(p + 2), a3 = __ldcs(p + 3);
+      const int4* p = reinterpret_cast<const int4*>(kc.col[j]) + base / 4 + lane;
+      int4 a[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = __ldcs(p + 32 * e);
       const KT m = (KT)kc.mult[j];
-      key[0] += (KT)(unsigned)a0.x * m; key[1] += (KT)(unsigned)a0.y * m; key[2] += (KT)(unsigned)a0.z * m; key[3] += (KT)(unsigned)a0.w * m;
-      key[4] += (KT)(unsigned)a1.x * m; key[5] += (KT)(unsigned)a1.y * m; key[6] += (KT)(unsigned)a1.z * m; key[7] += (KT)(unsigned)a1.w * m;
-      key[8] += (KT)(unsigned)a2.x * m; key[9] += (KT)(unsigned)a2.y * m; key[10] += (KT)(unsigned)a2.z * m; key[11] += (KT)(unsigned)a2.w * m;
-      key[12] += (KT)(unsigned)a3.x * m; key[13] += (KT)(unsigned)a3.y * m; key[14] += (KT)(unsigned)a3.z * m; key[15] += (KT)(unsigned)a3.w * m;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        key[4 * e] += (KT)(unsigned)a[e].x * m;
+        key[4 * e + 1] += (KT)(unsigned)a[e].y * m;
+        key[4 * e + 2] += (KT)(unsigned)a[e].z * m;
+        key[4 * e + 3] += (KT)(unsigned)a[e].w * m;
+      }
     }
   } else {
     for (int e = 0; e < FR; ++e) {
-      if (base + e >= n) break;
+      const int64_t r = base + 128 * (e >> 2) + 4 * lane + (e & 3);
+      if (r >= n) continue;
       KT k = 0;
       for (int j = 0; j < kc.K; ++j) {
-        unsigned v = j < kc.n_u8 ? (unsigned)reinterpret_cast<const uint8_t*>(kc.col[j])[base + e]
-                                 : (unsigned)reinterpret_cast<const int32_t*>(kc.col[j])[base + e];
+        unsigned v = j < kc.n_u8 ? (unsigned)reinterpret_cast<const uint8_t*>(kc.col[j])[r]
+                                 : (unsigned)reinterpret_cast<const int32_t*>(kc.col[j])[r];
         k += (KT)v * (KT)kc.mult[j];
       }
       key[e] = k;
     }
   }
 }
+#define FOLD_TILE_LOOP                                                                          \
+  const int lane = threadIdx.x & 31;                                                            \
+  const int64_t ntile = ceil_div64(n, FW);                                                      \
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;                               \
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntile; t += wstride)
+__device__ __forceinline__ int64_t tile_row(int64_t base, int lane, int e) { return base + 128 * (e >> 2) + 4 * lane + (e & 3); }
 
 // sort-path fallback (key space too large for a presence table): materialise the 64-bit keys
 __global__ void __launch_bounds__(256) k_fold_keys(KeyCols kc, int64_t n, bool vec, uint64_t* __restrict__ out) {
-  const int64_t nq = ceil_div64(n, FR);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+  FOLD_TILE_LOOP {
     unsigned long long key[FR];
-    fold_rows<unsigned long long>(kc, q, n, vec, key);
+    fold_tile<unsigned long long>(kc, t * FW, n, vec, lane, key);
 #pragma unroll
-    for (int e = 0; e < FR; ++e)
-      if (q * FR + e < n) out[q * FR + e] = key[e];
+    for (int e = 0; e < FR; ++e) {
+      const int64_t r = tile_row(t * FW, lane, e);
+      if (r < n) out[r] = key[e];
+    }
   }
 }
 // direct-address stage, pass 1: presence flags of the folded keys (the keys are never written out)
 __global__ void __launch_bounds__(256) k_fold_mark(KeyCols kc, int64_t n, bool vec, uint32_t* __restrict__ flags) {
-  const int64_t nq = ceil_div64(n, FR);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+  FOLD_TILE_LOOP {
     unsigned key[FR];
-    fold_rows<unsigned>(kc, q, n, vec, key);
+    fold_tile<unsigned>(kc, t * FW, n, vec, lane, key);
     // test before set: with few distinct keys and many rows, unconditional stores serialise on a few L2 lines
     // (a stale 0 from L1 only costs a redundant store; every writer stores 1)
 #pragma unroll
     for (int e = 0; e < FR; ++e)
-      if (q * FR + e < n && flags[key[e]] == 0u) flags[key[e]] = 1u;
+      if (tile_row(t * FW, lane, e) < n && flags[key[e]] == 0u) flags[key[e]] = 1u;
   }
 }
 // pass 2: recompute the key, look up its dense sorted rank
 __global__ void __launch_bounds__(256) k_fold_lookup(KeyCols kc, int64_t n, bool vec, const uint32_t* __restrict__ rank,
                                                      int32_t* __restrict__ gcode) {
-  const int64_t nq = ceil_div64(n, FR);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+  FOLD_TILE_LOOP {
     unsigned key[FR];
-    fold_rows<unsigned>(kc, q, n, vec, key);
-    if (vec && q * FR + FR - 1 < n) {
+    const int64_t base = t * FW;
+    fold_tile<unsigned>(kc, base, n, vec, lane, key);
+    if (vec && base + FW <= n) {
       int r[FR];
 #pragma unroll
       for (int e = 0; e < FR; ++e) r[e] = (int)__ldg(rank + key[e]);
-      int4* o = reinterpret_cast<int4*>(gcode) + q * 4;
+      int4* o = reinterpret_cast<int4*>(gcode) + base / 4 + lane;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) o[a] = make_int4(r[4 * a], r[4 * a + 1], r[4 * a + 2], r[4 * a + 3]);
+      for (int e = 0; e < 4; ++e) o[32 * e] = make_int4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
     } else {
-      for (int e = 0; e < FR; ++e)
-        if (q * FR + e < n) gcode[q * FR + e] = (int)rank[key[e]];
+      for (int e = 0; e < FR; ++e) {
+        const int64_t r = tile_row(base, lane, e);
+        if (r < n) gcode[r] = (int)rank[key[e]];
+      }
     }
   }
 }
@@ -186,6 +208,66 @@ __global__ void __launch_bounds__(PJ_T) k_group_stats(const int32_t* __restrict_
       }
     }
     segmented_flush<NS>(k, v, stats, 1, 0, G);
+  }
+}
+
+// Mid-size group counts (a few 10^4 groups, e.g. the 24 000 cells of BASELINE config 4) with unsorted keys: one RED
+// per row and statistic into L2 runs at ~170 G atomics/s.  Instead, one 1024-thread CTA per SM privatises a window
+// of [g0, g0 + B) groups x NS statistics in shared memory (up to 227 KB) and the rows are streamed once per window.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(1024, 1) k_group_stats_smem(const int32_t* __restrict__ key, const double* __restrict__ y,
+                                                              const double* __restrict__ w, int64_t n,
+                                                              double* __restrict__ stats, int64_t G, int g0, int B) {
+  constexpr int NS = WEIGHTED ? 3 : 2;
+  extern __shared__ double bins[];   // [NS][B]
+  for (int i = threadIdx.x; i < NS * B; i += blockDim.x) bins[i] = 0.0;
+  __syncthreads();
+  const int64_t nv = n / 4;
+  const int4* kv = reinterpret_cast<const int4*>(key);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = __ldcs(kv + q);
+    const double2 ya = __ldcs(reinterpret_cast<const double2*>(y) + 2 * q);
+    const double2 yb = __ldcs(reinterpret_cast<const double2*>(y) + 2 * q + 1);
+    const int cc[4] = {c.x - g0, c.y - g0, c.z - g0, c.w - g0};
+    const double yy[4] = {ya.x, ya.y, yb.x, yb.y};
+    double ww[4] = {1.0, 1.0, 1.0, 1.0};
+    if (WEIGHTED) {
+      const double2 wa = __ldcs(reinterpret_cast<const double2*>(w) + 2 * q);
+      const double2 wb = __ldcs(reinterpret_cast<const double2*>(w) + 2 * q + 1);
+      ww[0] = wa.x; ww[1] = wa.y; ww[2] = wb.x; ww[3] = wb.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if ((unsigned)cc[e] < (unsigned)B) {
+        if (WEIGHTED) {
+          atomicAdd(&bins[cc[e]], ww[e]);
+          atomicAdd(&bins[B + cc[e]], ww[e] * yy[e]);
+          atomicAdd(&bins[2 * B + cc[e]], ww[e] * yy[e] * yy[e]);
+        } else {
+          atomicAdd(&bins[cc[e]], yy[e]);
+          atomicAdd(&bins[B + cc[e]], yy[e] * yy[e]);
+        }
+      }
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const int c = key[i] - g0;
+      if ((unsigned)c < (unsigned)B) {
+        const double yv = y[i], wv = WEIGHTED ? w[i] : 1.0;
+        if (WEIGHTED) {
+          atomicAdd(&bins[c], wv);
+          atomicAdd(&bins[B + c], wv * yv);
+          atomicAdd(&bins[2 * B + c], wv * yv * yv);
+        } else {
+          atomicAdd(&bins[c], yv);
+          atomicAdd(&bins[B + c], yv * yv);
+        }
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * B; i += blockDim.x) {
+    const int q = i / B, g = i - q * B;
+    if (g0 + g < G && bins[i] != 0.0) atomicAdd(&stats[(size_t)q * G + g0 + g], bins[i]);
   }
 }
 
@@ -251,7 +333,7 @@ static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* k
     const int dt = key_dtypes ? key_dtypes[j] : LFE_I32;
     LFE_REQUIRE(dt == LFE_I32 || dt == LFE_U8, "lfe_compress: key column %d: dtype must be LFE_I32 or LFE_U8", j);
     LFE_REQUIRE(dt != LFE_U8 || n_groups[j] <= 256, "lfe_compress: uint8 key column %d needs n_groups <= 256", j);
-    vec = vec && (((uintptr_t)key_codes[j]) & (dt == LFE_U8 ? 15 : 63)) == 0;   // FR rows per aligned load group
+    vec = vec && (((uintptr_t)key_codes[j]) & (dt == LFE_U8 ? 3 : 15)) == 0;   // 32-bit / 128-bit loads
   }
   const int blocks = launch_blocks(h, ceil_div64(n, 256 * FR), 8);
   const bool want_keys = key_codes_out != nullptr;
@@ -318,7 +400,7 @@ static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* k
       k_fold_mark<<<blocks, 256, 0, s>>>(kc, n, vec, flags);
       KERNEL_CHECK();
       prim_exclusive_scan_u32(h, flags, rank, (int64_t)space, total, s);
-      k_fold_lookup<<<blocks, 256, 0, s>>>(kc, n, vec && (((uintptr_t)gcode.p) & 63) == 0, rank, gcode);
+      k_fold_lookup<<<blocks, 256, 0, s>>>(kc, n, vec && (((uintptr_t)gcode.p) & 15) == 0, rank, gcode);
       KERNEL_CHECK();
       uint32_t ht = 0;
       CUDA_CHECK(cudaMemcpyAsync(&ht, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -401,10 +483,31 @@ static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* k
     stats.zero();
     int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
     const bool vc = (((uintptr_t)gcode.p) & 15) == 0;
-    if (weights) k_group_stats<true><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, weights, n, stats, G, vc);
-    else k_group_stats<false><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, nullptr, n, stats, G, vc);
-    KERNEL_CHECK();
-    h->n_launches += 1;
+    // shared-memory windows when a few of them cover all groups and there are many rows per group
+    const int win = (int)(((size_t)h->smem_optin - 1024) / (NS * sizeof(double)));
+    const int64_t npass = win > 0 ? ceil_div64(G, win) : 1 << 30;
+    const bool aligned = vc && (((uintptr_t)y) & 15) == 0 && (!weights || (((uintptr_t)weights) & 15) == 0);
+    if (G > 4096 && npass <= 4 && n >= 64 * G && aligned) {
+      const int B = (int)ceil_div64(G, npass);
+      const size_t smem = (size_t)NS * B * sizeof(double);
+      static bool attr_set = false;
+      if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_group_stats_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        CUDA_CHECK(cudaFuncSetAttribute(k_group_stats_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        attr_set = true;
+      }
+      for (int64_t ps = 0; ps < npass; ++ps) {
+        if (weights) k_group_stats_smem<true><<<h->sm_count, 1024, smem, s>>>(gcode, y, weights, n, stats, G, (int)(ps * B), B);
+        else k_group_stats_smem<false><<<h->sm_count, 1024, smem, s>>>(gcode, y, nullptr, n, stats, G, (int)(ps * B), B);
+        KERNEL_CHECK();
+      }
+      h->n_launches += npass;
+    } else {
+      if (weights) k_group_stats<true><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, weights, n, stats, G, vc);
+      else k_group_stats<false><<<launch_blocks(h, nchunk, 8), PJ_T, 0, s>>>(gcode, y, nullptr, n, stats, G, vc);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
     const double* sy = stats.p + (weights ? G : 0);
     if (weights) CUDA_CHECK(cudaMemcpyAsync(n_out, stats.p, G * sizeof(double), cudaMemcpyDeviceToDevice, s));
     else prim_u32_to_f64(h, cnt, G, n_out, s);   // unweighted: _n is the exact integer group size

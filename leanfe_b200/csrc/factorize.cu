@@ -372,25 +372,43 @@ int64_t factorize_dispatch(lfe_ctx* h, const void* keys, int key_dtype, int64_t 
 // [min, max] of K integer key columns in one call (one sync): lets the caller use small raw values
 // (uint8 dummies) directly as group codes, radix = max + 1, instead of factorising every column.
 // ---------------------------------------------------------------------------------------------
+struct RangeCols {
+  const void* col[32];
+  int dtype[32];
+};
 template <typename T, typename V, int W>   // V = 16-byte vector of W elements of T
-__global__ void __launch_bounds__(256) k_range(const T* __restrict__ v, int64_t n, bool vec, long long* __restrict__ mm) {
-  long long lo = LLONG_MAX, hi = LLONG_MIN;
+__device__ __forceinline__ void range_scan(const T* __restrict__ v, int64_t n, long long& lo, long long& hi) {
+  const bool vec = (((uintptr_t)v) & 15) == 0;
   const int64_t nv = vec ? n / W : 0;
+  T tlo = (T)0, thi = (T)0;
+  bool any = false;
 #pragma unroll 4
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (int64_t)gridDim.x * blockDim.x) {
     V t = __ldcs(reinterpret_cast<const V*>(v) + q);
     const T* e = reinterpret_cast<const T*>(&t);
+    if (!any) { tlo = thi = e[0]; any = true; }
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      long long x = (long long)e[i];
-      lo = x < lo ? x : lo;
-      hi = x > hi ? x : hi;
+      tlo = e[i] < tlo ? e[i] : tlo;
+      thi = e[i] > thi ? e[i] : thi;
     }
   }
   for (int64_t i = nv * W + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    long long x = (long long)v[i];
-    lo = x < lo ? x : lo;
-    hi = x > hi ? x : hi;
+    T x = v[i];
+    if (!any) { tlo = thi = x; any = true; }
+    tlo = x < tlo ? x : tlo;
+    thi = x > thi ? x : thi;
+  }
+  if (any) { lo = (long long)tlo; hi = (long long)thi; }
+}
+// grid = (CTAs per column, K columns); one atomic pair per CTA
+__global__ void __launch_bounds__(256) k_ranges(RangeCols rc, int64_t n, long long* __restrict__ mm) {
+  const int j = blockIdx.y;
+  long long lo = LLONG_MAX, hi = LLONG_MIN;
+  switch (rc.dtype[j]) {
+    case LFE_U8: range_scan<uint8_t, uint4, 16>((const uint8_t*)rc.col[j], n, lo, hi); break;
+    case LFE_I32: range_scan<int32_t, int4, 4>((const int32_t*)rc.col[j], n, lo, hi); break;
+    default: range_scan<long long, longlong2, 2>((const long long*)rc.col[j], n, lo, hi); break;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -398,9 +416,21 @@ __global__ void __launch_bounds__(256) k_range(const T* __restrict__ v, int64_t 
     lo = a < lo ? a : lo;
     hi = c > hi ? c : hi;
   }
-  if ((threadIdx.x & 31) == 0 && lo <= hi) {
-    atomicMin(&mm[0], lo);
-    atomicMax(&mm[1], hi);
+  __shared__ long long slo[8], shi[8];
+  if ((threadIdx.x & 31) == 0) {
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      lo = slo[w] < lo ? slo[w] : lo;
+      hi = shi[w] > hi ? shi[w] : hi;
+    }
+    if (lo <= hi) {
+      atomicMin(&mm[2 * j], lo);
+      atomicMax(&mm[2 * j + 1], hi);
+    }
   }
 }
 
@@ -416,18 +446,23 @@ void key_ranges_impl(lfe_ctx* h, const void* const* cols, const int* dtypes, int
   DevBuf<long long> mm(2 * K, s);
   CUDA_CHECK(cudaMemcpyAsync(mm.p, init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaStreamSynchronize(s));   // init is a host stack/heap buffer
-  const int blocks = launch_blocks(h, ceil_div64(n > 0 ? n : 1, 256 * 16), 8);
-  for (int j = 0; j < K && n > 0; ++j) {
-    const bool vec = (((uintptr_t)cols[j]) & 15) == 0;
-    switch (dtypes[j]) {
-      case LFE_U8: k_range<uint8_t, uint4, 16><<<blocks, 256, 0, s>>>((const uint8_t*)cols[j], n, vec, mm.p + 2 * j); break;
-      case LFE_I32: k_range<int32_t, int4, 4><<<blocks, 256, 0, s>>>((const int32_t*)cols[j], n, vec, mm.p + 2 * j); break;
-      case LFE_I64: k_range<long long, longlong2, 2><<<blocks, 256, 0, s>>>((const long long*)cols[j], n, vec, mm.p + 2 * j); break;
-      default: LFE_THROW(LFE_ERR_ARG, "lfe_key_ranges: column %d: dtype must be LFE_U8, LFE_I32 or LFE_I64", j);
+  for (int j = 0; j < K; ++j)
+    LFE_REQUIRE(dtypes[j] == LFE_U8 || dtypes[j] == LFE_I32 || dtypes[j] == LFE_I64,
+                "lfe_key_ranges: column %d: dtype must be LFE_U8, LFE_I32 or LFE_I64", j);
+  for (int j0 = 0; j0 < K && n > 0; j0 += 32) {   // up to 32 columns per launch
+    const int kk = K - j0 < 32 ? K - j0 : 32;
+    RangeCols rc;
+    for (int j = 0; j < kk; ++j) {
+      rc.col[j] = cols[j0 + j];
+      rc.dtype[j] = dtypes[j0 + j];
     }
+    int bx = (8 * h->sm_count + kk - 1) / kk;
+    const int64_t need = ceil_div64(n, 256 * 16);
+    if (bx > need) bx = (int)need;
+    k_ranges<<<dim3(bx < 1 ? 1 : bx, kk), 256, 0, s>>>(rc, n, mm.p + 2 * j0);
     KERNEL_CHECK();
+    h->n_launches += 1;
   }
-  h->n_launches += K;
   if (h->world > 1) {   // the ranges of the whole (sharded) column; interleaved {min, max} pairs -> two strided passes
     std::vector<long long> tmp(2 * K);
     DevBuf<long long> lo(K, s), hi(K, s);

@@ -341,6 +341,29 @@ def test_compress_known_answer_from_reference_docstring(eng):
     np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), [5.0, 9.0])
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("n,g1,g2", [(700_003, 100, 70), (2_000_000, 300, 100)])
+def test_compress_midsize_group_counts_use_smem_windows(eng, weighted, n, g1, g2):
+    """A few 10^4 groups with many rows each: shared-memory histogram + windowed shared-memory statistics
+    (k_hist_smem_big / k_group_stats_smem) against the oracle; 1 to 4 windows."""
+    rng = np.random.default_rng(n + g1)
+    keys = [rng.integers(0, g1, n), rng.integers(0, g2, n)]
+    y = rng.normal(size=n) + 3.0
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    exp = O.compress(y, keys, w)
+    kc, Gs = zip(*[eng.factorize(dev(kcol))[:2] for kcol in keys])
+    got = eng.compress(list(kc), list(Gs), dev(y), dev(w) if weighted else None)
+    assert got["n_compressed"] == exp["n_compressed"] == g1 * g2
+    for a, b_ in zip(got["key_codes"], exp["key_codes"]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b_)
+    if not weighted:
+        np.testing.assert_array_equal(got["cnt"].cpu().numpy(), exp["n"].astype(np.int64))
+        np.testing.assert_array_equal(got["n"].cpu().numpy(), exp["n"])                    # exact integers
+    np.testing.assert_allclose(got["n"].cpu().numpy(), exp["n"], rtol=1e-12)
+    np.testing.assert_allclose(got["sum_y"].cpu().numpy(), exp["sum_y"], rtol=1e-11)
+    np.testing.assert_allclose(got["sum_y_sq"].cpu().numpy(), exp["sum_y_sq"], rtol=1e-11)
+
+
 @pytest.mark.parametrize("n", [5, 4099, 250_001])
 def test_compress_raw_uint8_keys_match_factorized_keys(eng, n):
     """uint8 key columns grouped on their raw values (no dictionary pass) give the same groups, counts and
