@@ -69,8 +69,10 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         raise ValueError("Must provide either 'formula' or (y_col, x_cols, fe_cols)")
     else:
         factor_vars, interactions, instruments = [], [], []
-    if instruments:
-        raise NotImplementedError("IV/2SLS is outside the scope of leanfe_b200 (SURVEY 8f.4)")
+    instruments = list(instruments)
+    if instruments and strategy == "compress":
+        # the reference's YOCO path takes no instruments and would silently fit OLS (compress.py:1049-1060)
+        raise ValueError("strategy='compress' does not support instruments; use 'alt_proj', 'demean' or 'ols'")
     if not isinstance(vcov, str) or vcov.lower() not in _VCOV:
         raise InvalidVcov(f"Invalid vcov method: {vcov}")
     vkind = _VCOV[vcov.lower()]
@@ -83,7 +85,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         raise ValueError(f"Unknown strategy: {strategy}")
 
     # needed columns (polars_impl.py:325-339)
-    needed = [y_col] + x_cols + fe_cols
+    needed = [y_col] + x_cols + fe_cols + [z for z in instruments if z not in x_cols + fe_cols + [y_col]]
     for var, _ in factor_vars:
         if var not in needed:
             needed.append(var)
@@ -112,6 +114,8 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             raise ValueError("multi-GPU fit: pass local_fe=<the FE column rows are sharded by>")
         if sample_frac is not None:
             raise NotImplementedError("sample_frac is not supported in multi-GPU fits")
+        if instruments:
+            raise NotImplementedError("IV/2SLS is single-GPU only")
         if cluster_cols and len(cluster_cols) > 1 and strategy != "compress":
             raise NotImplementedError("multi-way clustering is single-GPU only (except strategy='compress')")
 
@@ -149,6 +153,9 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             return t
         return num(name)
 
+    iv_state = {"k": None, "z_idx": []}
+    extra_z = [z for z in instruments if z not in x_cols]
+
     def columns(keep_int=False):
         """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
         y_ = num(y_col)
@@ -171,6 +178,14 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
                 if cat != ref_cat:
                     X_.append((kc.codes == j).to(torch.uint8 if keep_int else torch.float64))
                     names.append(f"{var}_{cat}")
+        # instruments ride along as extra columns: they are demeaned with y and X (polars_impl.py:431, 486); an
+        # exogenous regressor listed among the instruments is the same column, demeaned once
+        iv_state["k"] = len(names)
+        for z in instruments:
+            if z not in names:
+                X_.append(num(z))
+                names.append(z)
+        iv_state["z_idx"] = [names.index(z) for z in instruments]
         return y_, X_, names, w_
 
     cols_cache = []
@@ -184,8 +199,9 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     get_columns.owned = lambda t: id(t) in owned_ids
     if not interactions and not factor_vars and weights is None:
         # plain columns: they can be handed out one by one, as each upload completes
-        get_columns.lazy = dict(y=y_col, x=base_x, get=num,
-                                pending=lambda: any(nm in up.events for nm in [y_col] + base_x))
+        get_columns.lazy = dict(y=y_col, x=base_x + extra_z, get=num,
+                                pending=lambda: any(nm in up.events for nm in [y_col] + base_x + extra_z))
+        iv_state.update(k=len(base_x), z_idx=[(base_x + extra_z).index(z) for z in instruments])
 
     n0 = fe_keys[0].codes.numel() if fe_keys else get_columns()[0].numel()
 
@@ -209,6 +225,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         def ratio():
             # distinct rows over set(x_cols + fe_cols) / N   (compress.py:232-253)
             _, X, names, _ = get_columns()
+            names = names[: iv_state["k"]]
             kcs = []
             for nm in dict.fromkeys(names + fe_cols):
                 if nm in fe_cols:
@@ -223,7 +240,8 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
         if not fe_cols:
             est_ratio = ratio()
-            strategy = "ols" if est_ratio >= 0.8 else "compress"
+            # (with instruments the reference would pick 'compress' here and silently drop them; we fit 2SLS)
+            strategy = "ols" if est_ratio >= 0.8 or instruments else "compress"
         elif len(fe_cols) == 1:
             strategy = "demean"
         else:
@@ -233,7 +251,8 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
                 strategy = "alt_proj"
             else:
                 est_ratio = ratio()
-                strategy = determine_strategy(vcov, False, fe_card, MAX_FE_LEVELS, n0, len(get_columns()[2]), est_ratio)
+                strategy = determine_strategy(vcov, bool(instruments), fe_card, MAX_FE_LEVELS, n0,
+                                              iv_state["k"], est_ratio)
 
     if strategy == "compress":
         y, X, x_cols, w = cols_cache[0] if cols_cache else columns(keep_int=True)
@@ -244,7 +263,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
         w_early = num(weights) if weights is not None else None
         res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
-                       max_iter, formula, est_ratio, lf, cl_local)
+                       max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None)
     if profile:
         torch.cuda.synchronize(eng.device)
         res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
@@ -254,7 +273,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
 # ------------------------------------------------------------------------------------------------
 def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
-             formula, est_ratio, local_fe=-1, cl_local=False) -> LeanFEResult:
+             formula, est_ratio, local_fe=-1, cl_local=False, iv=None) -> LeanFEResult:
     """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression.
 
     ``get_columns()`` -> (y, X, names, w) is called as late as possible: the singleton test and the demean plan
@@ -338,6 +357,18 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         k = len(X)
         cols = [y] + list(X)
         n_obs = cols[0].numel()
+    if iv is not None:
+        # 2SLS instead of OLS (polars_impl.py:176-198); iv["z_idx"] picks the (demeaned) instrument columns
+        k = iv["k"]
+        Z = [cols[1 + i] for i in iv["z_idx"]]
+        beta, se, rss, df_resid, n_clusters = _regress_iv(eng, cols[0], cols[1:1 + k], Z, w, vkind, cl_codes,
+                                                          [c.n_groups for c in cl_keys], ssc, n_obs, absorbed)
+        x_cols, n_instr = list(x_cols)[:k], len(Z)
+        return LeanFEResult(coefs=dict(zip(x_cols, beta)), std_errors=dict(zip(x_cols, se)), n_obs=n_obs,
+                            iterations=iterations, vcov_type=vcov, is_iv=True, n_instruments=n_instr,
+                            n_clusters=n_clusters, df_resid=df_resid, formula=formula, fe_cols=fe_cols, fe_dims=fe_dims,
+                            r_squared=None, compression_ratio=est_ratio, rss=rss, strategy=strategy,
+                            converged=converged)
     if vkind == capi.VCOV_CLUSTER and cl_local:
         vkind |= capi.VCOV_CLUSTER_LOCAL
     # regression on [1 | X~] (polars_impl.py:166-226)
@@ -359,6 +390,61 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
                         df_resid=df_resid, formula=formula, fe_cols=fe_cols, fe_dims=fe_dims, r_squared=r2,
                         compression_ratio=est_ratio, rss=float(rss), tss=float(tss), strategy=strategy,
                         converged=converged)
+
+
+def _regress_iv(eng: Engine, y, X, Z, w, vkind, cl_codes, cl_G, ssc, n_obs, absorbed):
+    """2SLS exactly as the reference runs it (polars_impl.py:176-198, 229-278; common.py:188-287;
+    std_errors.py:448-598): EVERY column of X = [1 | x] is projected on the instruments Z (a constant joins Z
+    only when Z has fewer columns than X), beta = (Xh'Xh)^-1 Xh'y, residuals are taken with the FITTED Xh, and
+    the sandwiches use Xh.  On the device this needs no n x k temporary: with gamma = (Z'WZ)^-1 Z'WX,
+
+        Xh'WXh = gamma' Z'WZ gamma,   Xh'Wy = gamma' Z'Wy,   resid = y - Z (gamma beta),
+        V = A V_Z A',  A = (Xh'WXh)^-1 gamma',
+
+    where V_Z is the ordinary meat (HC1 / one-way / multi-way, with the same scalar corrections) of the
+    regressor set Z -- one Gram pass over [1, x, z, y] and one lfe_resid_vcov pass over [y, Z].
+    -> (beta[k], se[k], rss, df_resid, n_clusters)"""
+    k, m = len(X), len(Z)
+    n = y.numel()
+    add_const = (k + 1) > m and not any(bool(((z - 1.0).abs() <= 1e-8 + 1e-5).all()) for z in Z)   # np.allclose(col, 1)
+    mz = m + (1 if add_const else 0)
+    if mz < k + 1:
+        raise ValueError(f"Under-identified: {mz} instruments for {k + 1} endogenous variables")
+    gram = eng.gram(list(X) + list(Z) + [y], w, add_intercept=True)        # order: 1, x.., z.., y
+    ix = torch.arange(0, k + 1, device=eng.device)
+    iz = torch.tensor(([0] if add_const else []) + list(range(k + 1, k + 1 + m)), device=eng.device)
+    iy = k + 1 + m
+    ZtZ = gram.index_select(0, iz).index_select(1, iz).contiguous()
+    ZtX = gram.index_select(0, iz).index_select(1, ix).contiguous()
+    ZtY = gram.index_select(0, iz)[:, iy].contiguous()
+    _, ZtZ_inv, _ = eng.solve_spd(ZtZ, ZtY)
+    gamma = ZtZ_inv @ ZtX                                                  # first stage, (mz, k+1)
+    XhXh = gamma.T @ ZtZ @ gamma
+    XhXh = (0.5 * (XhXh + XhXh.T)).contiguous()
+    beta_full, XtX_inv, _ = eng.solve_spd(XhXh, (gamma.T @ ZtY).contiguous())
+    delta = gamma @ beta_full                                              # resid = y - Z delta
+    df_resid = n_obs - (k + 1) - absorbed
+    kind = vkind & 0xFF
+    if kind == capi.VCOV_IID:
+        b_z = delta if add_const else torch.cat([torch.zeros(1, dtype=torch.float64, device=eng.device), delta])
+        out = eng.resid_vcov([y] + list(Z), b_z.contiguous(), torch.eye(m, dtype=torch.float64, device=eng.device),
+                             capi.VCOV_IID, None, None, w, ssc, n_obs, df_resid)
+        V = XtX_inv * (out["stats"][2] / df_resid)                         # std_errors.py:183-210 on the full (X'X)^-1
+        n_clusters = None
+    else:
+        Zc = ([torch.ones(n, dtype=torch.float64, device=eng.device)] if add_const else []) + list(Z)
+        b_z = torch.cat([torch.zeros(1, dtype=torch.float64, device=eng.device), delta]).contiguous()
+        out = eng.resid_vcov([y] + Zc, b_z, torch.eye(mz, dtype=torch.float64, device=eng.device), kind, cl_codes, cl_G,
+                             w, ssc, n_obs, df_resid)
+        A = XtX_inv @ gamma.T
+        V = A @ out["vcov"] @ A.T
+        n_clusters = None
+        if kind == capi.VCOV_CLUSTER:
+            n_clusters = out["n_clusters"][0] if len(cl_G) == 1 else tuple(out["n_clusters"])
+    se_full = torch.sqrt(torch.clamp(torch.diagonal(V), min=0.0))
+    host = torch.cat([beta_full, se_full, out["stats"][:1]]).cpu().numpy()
+    p = k + 1
+    return host[1:p].tolist(), host[p + 1:2 * p].tolist(), float(host[2 * p]), df_resid, n_clusters
 
 
 def _fit_compress(eng: Engine, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n_obs):

@@ -329,6 +329,68 @@ def standard_errors(vcov, X, B, resid, w, clusters, n_obs, df_resid, ssc):
 
 
 # ---------------------------------------------------------------------------
+# IV / 2SLS  (common.py:188-287, polars_impl.py:176-198 / 229-278, std_errors.py:448-598)
+# ---------------------------------------------------------------------------
+def iv_2sls(Y, X, Z, w=None):
+    """common.py:188-287.  X (n x p) are ALL treated as endogenous and regressed on Z (n x m), m >= p."""
+    if Z.shape[1] < X.shape[1]:
+        raise ValueError(f"Under-identified: {Z.shape[1]} instruments for {X.shape[1]} endogenous variables")
+    if w is not None:                                              # :251-274
+        sw = np.sqrt(w)
+        Zw, Xw, Yw = Z * sw[:, None], X * sw[:, None], Y * sw
+        gamma = np.linalg.solve(Zw.T @ Zw, Zw.T @ Xw)
+        Xh = Z @ gamma
+        Xhw = Xh * sw[:, None]
+        beta = np.linalg.solve(Xhw.T @ Xhw, Xhw.T @ Yw)
+    else:                                                          # :277-287
+        gamma = np.linalg.solve(Z.T @ Z, Z.T @ X)
+        Xh = Z @ gamma
+        beta = np.linalg.solve(Xh.T @ Xh, Xh.T @ Y)
+    return beta, Xh
+
+
+def run_regression_iv(y, X, Z, w, n_obs, absorbed_df):
+    """polars_impl.py:166-198, 229-232 with instruments.  X, Z WITHOUT intercept.  The intercept column is one of
+    the 'endogenous' columns; a constant joins Z only if Z has fewer columns than [1 | X] and no constant
+    column (:179-182).  Residuals use the FITTED Xh (:229), (X'X)^-1 is (Xh'WXh)^-1 (:187-198)."""
+    k = X.shape[1]
+    Xi = np.hstack([np.ones((X.shape[0], 1)), X]) if k > 0 else np.ones((n_obs, 1))
+    Zi = Z
+    if Xi.shape[1] > Zi.shape[1]:
+        if not any(np.allclose(col, 1.0) for col in Zi.T):
+            Zi = np.column_stack([np.ones(Zi.shape[0]), Zi])
+    beta_full, Xh = iv_2sls(y, Xi, Zi, w)
+    A = (Xh * np.sqrt(w)[:, None]).T @ (Xh * np.sqrt(w)[:, None]) if w is not None else Xh.T @ Xh
+    try:
+        L = np.linalg.cholesky(A)
+        XtX_inv = np.linalg.solve(L.T, np.linalg.solve(L, np.eye(L.shape[0])))
+    except np.linalg.LinAlgError:
+        XtX_inv = np.linalg.inv(A)
+    resid = y - Xh @ beta_full
+    df_resid = n_obs - (k + 1) - absorbed_df
+    return dict(beta_full=beta_full, beta=beta_full[1:], XtX_inv=XtX_inv, Xh=Xh, resid=resid, df_resid=df_resid,
+                rss=float(np.sum(resid ** 2)), n_z=Zi.shape[1])
+
+
+def standard_errors_iv(vcov, Xh, XtX_inv, resid, w, clusters, n_obs, df_resid, ssc):
+    """std_errors.py:85-145 dispatch with is_iv=True -> :183-210 (iid, full (X'X)^-1) and :448-598 (hc1,
+    one-way, multi-way on Xh).  The IV variants use the same sandwich algebra and scalar corrections as the
+    OLS ones, applied to Xh and the full inverse; the caller strips the intercept entry (polars_impl.py:271-274)."""
+    v = vcov.lower()
+    if v == "iid":
+        return se_iid(XtX_inv, resid, w, df_resid), None
+    if v == "hc1":
+        return se_hc1(Xh, XtX_inv, resid, w, n_obs, df_resid)[0], None
+    if not clusters:
+        raise ValueError("cluster_cols required for vcov='cluster'")
+    if len(clusters) == 1:
+        se, G, _ = se_cluster_oneway(Xh, XtX_inv, resid, w, clusters[0], n_obs, df_resid, ssc)
+        return se, G
+    se, Gs, _ = se_cluster_multiway(Xh, XtX_inv, resid, w, clusters, n_obs, df_resid, ssc)
+    return se, Gs
+
+
+# ---------------------------------------------------------------------------
 # (a13-a18) YOCO  (compress.py)
 # ---------------------------------------------------------------------------
 def determine_strategy(vcov, has_instruments, fe_cardinality=None, max_fe_levels=MAX_FE_LEVELS,
@@ -533,8 +595,9 @@ def leanfe_oracle(data: dict, y_col=None, x_cols=None, fe_cols=None, formula=Non
         raise ValueError("Must provide either 'formula' or (y_col, x_cols, fe_cols)")
     else:
         factor_vars, interactions, instruments = [], [], []
-    if instruments:
-        raise NotImplementedError("IV/2SLS is out of scope (SURVEY 8f.4)")
+    instruments = list(instruments)
+    if instruments and strategy == "compress":
+        raise ValueError("strategy='compress' does not support instruments")
     if vcov.lower() not in ("iid", "hc1", "cluster"):
         raise ValueError(f"Invalid vcov method: {vcov}")
     x_cols, fe_cols = list(x_cols), list(fe_cols or [])
@@ -558,15 +621,16 @@ def leanfe_oracle(data: dict, y_col=None, x_cols=None, fe_cols=None, formula=Non
     if strategy == "auto":
         est_ratio = estimate_compression_ratio([np.asarray(data[c]) for c in dict.fromkeys(x_cols + fe_cols)])
         if not fe_cols:
-            strategy = "ols" if est_ratio >= 0.8 else "compress"
+            strategy = "ols" if est_ratio >= 0.8 or instruments else "compress"
         elif len(fe_cols) == 1:
             strategy = "demean"
         else:
-            strategy = determine_strategy(vcov, False, dict(zip(fe_cols, fe_card)), MAX_FE_LEVELS,
+            strategy = determine_strategy(vcov, bool(instruments), dict(zip(fe_cols, fe_card)), MAX_FE_LEVELS,
                                           n0, len(x_cols), est_ratio)
     w_full = np.asarray(data[weights], dtype=np.float64) if weights is not None else None
     y_full = np.asarray(data[y_col], dtype=np.float64)
-    X_full = [np.asarray(data[c], dtype=np.float64) for c in x_cols]
+    X_full = [np.asarray(data[c], dtype=np.float64) for c in x_cols + instruments]   # instruments demeaned too (:486)
+    n_z = len(instruments)
 
     if strategy == "compress":
         cl = list(cluster_cols) if cluster_cols else []
@@ -614,8 +678,20 @@ def leanfe_oracle(data: dict, y_col=None, x_cols=None, fe_cols=None, formula=Non
     n_obs = int(keep.sum())
     y = cols[0]
     X = np.column_stack(cols[1:]) if len(cols) > 1 else np.zeros((n_obs, 0))
-    reg = run_regression(y, X, w, n_obs, absorbed)
     clusters = [np.asarray(data[c])[keep] for c in cluster_cols] if cluster_cols else None
+    if n_z:
+        X, Z = X[:, : X.shape[1] - n_z], X[:, X.shape[1] - n_z:]
+        reg = run_regression_iv(y, X, Z, w, n_obs, absorbed)
+        se_full, n_clusters = standard_errors_iv(vcov, reg["Xh"], reg["XtX_inv"], reg["resid"], w, clusters, n_obs,
+                                                 reg["df_resid"], ssc)
+        out = dict(coefs=dict(zip(x_cols, reg["beta"])), std_errors=dict(zip(x_cols, se_full[1:])), n_obs=n_obs,
+                   iterations=iterations, vcov_type=vcov, n_clusters=n_clusters, df_resid=reg["df_resid"],
+                   fe_dims=fe_dims, r_squared=None, compression_ratio=est_ratio, strategy=strategy,
+                   n_compressed=None, rss=reg["rss"], is_iv=True, n_instruments=n_z)
+        if return_internals:
+            out.update(_reg=reg, _cols=cols, _keep=keep, _max_mean=max_mean, _w=w)
+        return out
+    reg = run_regression(y, X, w, n_obs, absorbed)
     se, n_clusters = standard_errors(vcov, X, reg["B"], reg["resid"], w, clusters, n_obs, reg["df_resid"], ssc)
     out = dict(coefs=dict(zip(x_cols, reg["beta"])), std_errors=dict(zip(x_cols, se)), n_obs=n_obs,
                iterations=iterations, vcov_type=vcov, n_clusters=n_clusters, df_resid=reg["df_resid"],

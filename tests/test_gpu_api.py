@@ -105,6 +105,48 @@ def test_yoco_golden_reference_solver(golden_dir, vcov, ssc, cl):
     assert res.strategy == "compress" and res.iterations == 0 and res.fe_dims == (40, 8)
 
 
+IV_CASES = [  # (tag, strategy, weights, vcov, cluster_cols, ssc)
+    ("exact_iid", "alt_proj", None, "iid", None, True), ("exact2_hc1", "alt_proj", None, "hc1", None, True),
+    ("exact2_cl", "alt_proj", None, "cluster", ["unit"], True),
+    ("exact2_cl_nossc_w", "alt_proj", "w", "cluster", ["unit"], False),
+    ("exact2_2way", "alt_proj", None, "cluster", ["unit", "st"], True),
+    ("exact_iid_w_onefe", "demean", "w", "iid", None, True), ("nofe_hc1", "ols", None, "hc1", None, True),
+    ("nofe_over_iid", "ols", None, "iid", None, True),
+]
+
+
+@pytest.mark.parametrize("tag,strategy,wname,vcov,cl,ssc", IV_CASES)
+def test_iv_2sls_golden_reference_functions(golden_dir, tag, strategy, wname, vcov, cl, ssc):
+    """IV/2SLS (formula 'y ~ x | fe | z') against the reference's own iv_2sls / _compute_se_*_iv outputs."""
+    from leanfe_b200 import leanfe
+    g = _golden(golden_dir, "iv.npz")
+    d = {k: g[k] for k in ("y", "x1", "x2", "z1", "z2", "unit", "time", "w", "st")}
+    res = leanfe(d, formula=str(g[f"formula_{tag}"]), strategy=strategy, weights=wname, vcov=vcov, cluster_cols=cl,
+                 ssc=ssc, demean_tol=1e-13, max_iter=2000)
+    np.testing.assert_allclose(list(res.coefs.values()), g[f"ref_beta_{tag}"], rtol=RTOL_BETA)
+    np.testing.assert_allclose(list(res.std_errors.values()), g[f"ref_se_{tag}"], rtol=RTOL_SE)
+    assert res.df_resid == int(g[f"ref_df_resid_{tag}"])
+    assert res.rss == pytest.approx(float(g[f"ref_rss_{tag}"]), rel=1e-8)
+    assert res.is_iv and res.n_instruments == str(g[f"formula_{tag}"]).split("|")[2].count("+") + 1
+    assert res.r_squared is None
+    ncl = g[f"ref_ncl_{tag}"]
+    if cl is not None:
+        assert res.n_clusters == (int(ncl) if ncl.ndim == 0 else tuple(int(v) for v in ncl))
+
+
+def test_iv_default_tolerance_matches_oracle_and_rejects_bad_requests(golden_dir):
+    from leanfe_b200 import leanfe
+    g = _golden(golden_dir, "iv.npz")
+    d = {k: g[k] for k in ("y", "x1", "x2", "z1", "z2", "unit", "time", "w", "st")}
+    kw = dict(formula="y ~ x1 + x2 | unit + time | z1 + x2", vcov="cluster", cluster_cols=["unit"])
+    res, ref = leanfe(d, **kw), O.leanfe_oracle(d, **kw)          # strategy='auto' -> alt_proj, default tol / max_iter
+    _check(res, ref)
+    with pytest.raises(ValueError, match="Under-identified"):
+        leanfe(d, formula="y ~ x1 + x2 | unit | z1")
+    with pytest.raises(ValueError, match="instruments"):
+        leanfe(d, formula="y ~ x1 | unit + time | z1", strategy="compress")
+
+
 def _c1(balanced: bool, N=1_000_000):
     """BASELINE config 1: 1M rows, y ~ x1 + x2 | unit(10k) + time(100), IID."""
     rng = np.random.default_rng(42)
@@ -254,8 +296,8 @@ def test_degenerate_inputs_raise_cleanly():
         leanfe(d, formula="y ~ x | u + t")                  # every unit is a singleton: nothing left to fit
     with pytest.raises(KeyError):
         leanfe(d, formula="y ~ nope | t")
-    with pytest.raises(NotImplementedError):
-        leanfe(d, formula="y ~ x | t | z")                  # IV is out of scope, says so
+    with pytest.raises(KeyError):
+        leanfe(d, formula="y ~ x | t | z")                  # unknown instrument column
 
 
 def test_wide_design_twenty_regressors():

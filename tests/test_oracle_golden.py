@@ -109,6 +109,32 @@ def test_yoco_equals_fwl_identity(golden_dir):
     np.testing.assert_allclose(list(a["std_errors"].values()), list(b["std_errors"].values()), rtol=1e-9)
 
 
+IV_CASES = [  # (tag, strategy, weights, vcov, cluster_cols, ssc) -- formulas are stored in the fixture
+    ("exact_iid", "alt_proj", None, "iid", None, True), ("exact2_hc1", "alt_proj", None, "hc1", None, True),
+    ("exact2_cl", "alt_proj", None, "cluster", ["unit"], True),
+    ("exact2_cl_nossc_w", "alt_proj", "w", "cluster", ["unit"], False),
+    ("exact2_2way", "alt_proj", None, "cluster", ["unit", "st"], True),
+    ("exact_iid_w_onefe", "demean", "w", "iid", None, True), ("nofe_hc1", "ols", None, "hc1", None, True),
+    ("nofe_over_iid", "ols", None, "iid", None, True),
+]
+
+
+def test_iv_2sls_against_reference_functions(golden_dir):
+    """IV: the restatement against common.iv_2sls + std_errors._compute_se_*_iv of the unmodified reference
+    (tests/golden/make_golden_iv.py)."""
+    g = _load(golden_dir, "iv.npz")
+    d = {k: g[k] for k in ("y", "x1", "x2", "z1", "z2", "unit", "time", "w", "st")}
+    for tag, strategy, wname, vc, cl, ssc in IV_CASES:
+        r = O.leanfe_oracle(d, formula=str(g[f"formula_{tag}"]), strategy=strategy, weights=wname, vcov=vc,
+                            cluster_cols=cl, ssc=ssc, demean_tol=1e-13, max_iter=2000)
+        np.testing.assert_allclose(np.array(list(r["coefs"].values())), g[f"ref_beta_{tag}"], rtol=1e-9)
+        np.testing.assert_allclose(np.array(list(r["std_errors"].values())), g[f"ref_se_{tag}"], rtol=1e-8)
+        assert r["df_resid"] == int(g[f"ref_df_resid_{tag}"]) and r["is_iv"] and r["r_squared"] is None
+        np.testing.assert_allclose(r["rss"], float(g[f"ref_rss_{tag}"]), rtol=1e-9)
+    with pytest.raises(ValueError, match="Under-identified"):
+        O.leanfe_oracle(d, formula="y ~ x1 + x2 | unit | z1", strategy="demean")        # 2 instruments (1 + z1) < 3
+
+
 def test_reference_docstring_known_answers():
     # compress.py:222-225 ; compress.py:318-323 ; compress.py:835-840
     assert O.estimate_compression_ratio([np.array([1, 1, 2]), np.array([1, 1, 2])]) == pytest.approx(2 / 3)
