@@ -152,6 +152,9 @@ void prim_argsort_u32(lfe_ctx* h, const uint32_t* keys, int64_t n, int key_bits,
                       uint32_t* keys_sorted_out, cudaStream_t s);
 void prim_sort_pairs_u32(lfe_ctx* h, const uint32_t* keys, const uint32_t* vals_in, int64_t n, int key_bits,
                          uint32_t* keys_out, uint32_t* vals_out, cudaStream_t s);
+// keys only, sorted (stably) on bits [bit_lo, bit_lo + key_bits)
+void prim_sort_keys_u32(lfe_ctx* h, const uint32_t* keys, int64_t n, int bit_lo, int key_bits, uint32_t* keys_out,
+                        cudaStream_t s);
 void prim_argsort_u64(lfe_ctx* h, const uint64_t* keys, int64_t n, int key_bits, uint32_t* perm_out,
                       uint64_t* keys_sorted_out, cudaStream_t s);
 // counts[g] = #codes == g

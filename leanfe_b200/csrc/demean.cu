@@ -29,19 +29,38 @@ constexpr int PJ_NB = 2;  // sub-batches of PJ_I entries per thread: 8 consecuti
 
 // One sub-batch: keys + gathered/summed rows of the other FEs' tables.  FULL = all 4 entries exist (no bounds
 // or validity branches, so the compiler hoists all 128-bit gathers ahead of the first use).
-template <int NC, bool WEIGHTED, bool FULL>
+// PACKED: `key` is the two-FE entry list of packed words (pk.kshift/kmask select this FE's code,
+// pk.oshift/omask the other FE's), one 4-byte stream instead of two.
+struct PackSpec {
+  int kshift, oshift;
+  uint32_t kmask, omask;
+};
+
+template <int NC, bool WEIGHTED, bool FULL, bool PACKED>
 __device__ __forceinline__ void proj_batch(const int32_t* __restrict__ key, const ProjOthers& oth,
                                            const double* const tabs[LFE_MAX_FE], const double* __restrict__ w,
                                            int64_t base, int64_t n, int ldc, int col0, bool vec_codes, bool vec2,
-                                           int k[PJ_I], double v[PJ_I][NC]) {
-  load4_i32(key, base, n, vec_codes && FULL, k);
+                                           const PackSpec& pk, int k[PJ_I], double v[PJ_I][NC]) {
+  int pw[PJ_I];
+  load4_i32(key, base, n, vec_codes && FULL, PACKED ? pw : k);
+  if (PACKED) {
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e)
+      k[e] = (FULL || base + e < n) ? (int)(((uint32_t)pw[e] >> pk.kshift) & pk.kmask) : -1;
+  }
 #pragma unroll
   for (int e = 0; e < PJ_I; ++e)
 #pragma unroll
     for (int c = 0; c < NC; ++c) v[e][c] = 0.0;
   for (int o = 0; o < oth.n; ++o) {
     int oc[PJ_I];
-    load4_i32(oth.code[o], base, n, vec_codes && FULL, oc);
+    if (PACKED) {
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e)
+        oc[e] = (FULL || base + e < n) ? (int)(((uint32_t)pw[e] >> pk.oshift) & pk.omask) : -1;
+    } else {
+      load4_i32(oth.code[o], base, n, vec_codes && FULL, oc);
+    }
     const double* tab = tabs[o] + col0;   // global (L2-resident) or the CTA's shared-memory copy
 #pragma unroll
     for (int e = 0; e < PJ_I; ++e) {
@@ -71,10 +90,11 @@ __device__ __forceinline__ void proj_batch(const int32_t* __restrict__ key, cons
   }
 }
 
-template <int NC, bool WEIGHTED>
+template <int NC, bool WEIGHTED, bool PACKED>
 __global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
                                                const double* __restrict__ w, int64_t n, int ldc, int col0,
-                                               double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes) {
+                                               double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes,
+                                               PackSpec pk) {
   constexpr int PER_THREAD = PJ_I * PJ_NB;
   extern __shared__ double sm_tabs[];
   const double* tabs[LFE_MAX_FE];
@@ -92,14 +112,14 @@ __global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ ke
       for (int b = 0; b < PJ_NB; ++b) {
         int k[PJ_I];
         double v[PJ_I][NC];
-        proj_batch<NC, WEIGHTED, true>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, k, v);
+        proj_batch<NC, WEIGHTED, true, PACKED>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, pk, k, v);
         run_fold<NC>(cur, run, k, v, acc, ld_acc, acc_col0);
       }
     } else {
       for (int b = 0; b < PJ_NB; ++b) {
         int k[PJ_I];
         double v[PJ_I][NC];
-        proj_batch<NC, WEIGHTED, false>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, k, v);
+        proj_batch<NC, WEIGHTED, false, PACKED>(key, oth, tabs, w, tbase + b * PJ_I, n, ldc, col0, vec_codes, vec2, pk, k, v);
         run_fold<NC>(cur, run, k, v, acc, ld_acc, acc_col0);
       }
     }
@@ -209,6 +229,13 @@ __global__ void __launch_bounds__(256) k_u32_to_f64(const uint32_t* __restrict__
     out[i] = (double)in[i];
 }
 
+// words[i] = (big[i] << bs) | small[i]
+__global__ void __launch_bounds__(256) k_pack_codes(const int32_t* __restrict__ big, const int32_t* __restrict__ small,
+                                                    int64_t n, int bs, uint32_t* __restrict__ words) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    __stcs(words + i, ((uint32_t)__ldcs(big + i) << bs) | (uint32_t)__ldcs(small + i));
+}
+
 // cols[c][i] -= sum_j alpha_j[code_j[i]][col0 + c]
 typedef ProjOthers ApplyTabs;   // code[j] in ROW order here; small tables are staged in shared memory too
 template <int NC>
@@ -254,6 +281,8 @@ struct FEState {
   const int32_t* key = nullptr;
   DevBuf<int32_t> oth_buf[LFE_MAX_FE];
   const int32_t* oth[LFE_MAX_FE] = {nullptr};
+  bool packed = false;   // key_buf holds packed (big code << bs | small code) words, see demean_plan_create
+  PackSpec pk = {0, 0, 0u, 0u};
   DevBuf<double> w_buf;
   const double* w = nullptr;
   DevBuf<double> alpha, S0, acc, nsum, cnt_buf, S0u_buf, acc_chk;
@@ -285,10 +314,16 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
   int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I * PJ_NB);
   int blocks = launch_blocks(h, nchunk, 2);   // persistent: 2 CTAs per SM (register-limited), tables staged once
   bool vec = aligned16(st.key);
-  for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
-#define PJ_CASE(NC_)                                                                                                \
-  case NC_:                                                                                                         \
-    k_proj<NC_, WEIGHTED><<<blocks, PJ_T, smem, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc, acc_col0, vec); \
+  if (!st.packed)
+    for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
+#define PJ_CASE(NC_)                                                                                          \
+  case NC_:                                                                                                   \
+    if (st.packed)                                                                                            \
+      k_proj<NC_, false, true><<<blocks, PJ_T, smem, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc,      \
+                                                          acc_col0, vec, st.pk);                             \
+    else                                                                                                      \
+      k_proj<NC_, WEIGHTED, false><<<blocks, PJ_T, smem, s>>>(st.key, oth, st.w, n, ldc, col0, acc, ld_acc,  \
+                                                              acc_col0, vec, st.pk);                         \
     break;
   switch (nc) {
     PJ_CASE(1) PJ_CASE(2) PJ_CASE(3) PJ_CASE(4) PJ_CASE(5) PJ_CASE(6) PJ_CASE(7) PJ_CASE(8)
@@ -400,8 +435,32 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
       LFE_REQUIRE(st[j].G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
       st[j].identity = (F == 1) || prim_is_sorted(h, codes[j], n, s) != 0;   // F == 1 never projects
     }
-    if (F == 2 && !weighted && !st[0].identity && !st[1].identity) {
-      // two FEs: sort (key, other code) pairs directly -- no row permutation, no gathers
+    if (F == 2 && !weighted && !st[0].identity && !st[1].identity &&
+        bits_for((uint64_t)(st[0].G - 1)) + bits_for((uint64_t)(st[1].G - 1)) <= 32) {
+      // two FEs whose codes fit one 32-bit word together: every entry is the packed word
+      // (big code << bs) | small code.  Sorting the words stably on the big code's bits gives the big FE's
+      // entry list, sorting THAT stably on the small code's bits gives the small FE's (big codes ascending
+      // inside every small group) -- keys only, no payload, no row permutation, no gathers, and each
+      // projection streams 4 bytes per entry.
+      const int sm = 1 - big;
+      FEState &B = st[big], &M = st[sm];
+      const int bs = bits_for((uint64_t)(M.G - 1)), bb = bits_for((uint64_t)(B.G - 1));
+      const uint32_t smask = bs >= 32 ? 0xffffffffu : ((1u << bs) - 1u);
+      const uint32_t bmask = bb >= 32 ? 0xffffffffu : ((1u << bb) - 1u);
+      DevBuf<int32_t> words(n, s);
+      k_pack_codes<<<launch_blocks(h, ceil_div64(n, 256 * 4), 8), 256, 0, s>>>(codes[big], codes[sm], n, bs,
+                                                                                (uint32_t*)words.p);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      B.key_buf.alloc(n, s);
+      prim_sort_keys_u32(h, (const uint32_t*)words.p, n, bs, bb, (uint32_t*)B.key_buf.p, s);
+      M.key_buf.alloc(n, s);
+      prim_sort_keys_u32(h, (const uint32_t*)B.key_buf.p, n, 0, bs, (uint32_t*)M.key_buf.p, s);
+      B.key = B.key_buf; B.packed = true; B.pk = PackSpec{bs, 0, bmask, smask};
+      M.key = M.key_buf; M.packed = true; M.pk = PackSpec{0, bs, smask, bmask};
+      B.oth[sm] = nullptr; M.oth[big] = nullptr;
+    } else if (F == 2 && !weighted && !st[0].identity && !st[1].identity) {
+      // two FEs, codes too wide to pack: sort (key, other code) pairs directly
       const int sm = 1 - big;
       FEState &B = st[big], &M = st[sm];
       B.key_buf.alloc(n, s); B.oth_buf[sm].alloc(n, s);

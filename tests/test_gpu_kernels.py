@@ -128,6 +128,29 @@ def test_sort_rows_radix_widths(eng, G):
     np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(a, kind="stable"))
 
 
+@pytest.mark.parametrize("kind", ["random", "constant", "sorted", "two_values", "zipf"])
+def test_sort_rows_large_multi_tile_and_skewed(eng, kind):
+    # 20.5M rows: the sort walks 4 tiles per CTA (running digit offsets) and the last CTA is ragged
+    rng = np.random.default_rng(5)
+    n = 20_500_003
+    G = 1_500_000          # 21 bits -> two 11-bit passes
+    if kind == "random":
+        a = rng.integers(0, G, n)
+    elif kind == "constant":
+        a = np.full(n, G - 1)
+    elif kind == "sorted":
+        a = np.sort(rng.integers(0, G, n))
+    elif kind == "two_values":
+        a = rng.integers(0, 2, n) * (G - 1)
+    else:
+        a = np.minimum(rng.zipf(1.3, n) - 1, G - 1)
+    a = a.astype(np.int32)
+    perm, was_sorted = eng.sort_rows(dev(a), G)
+    if kind in ("constant", "sorted"):
+        assert was_sorted
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(a, kind="stable"))
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) demean
 # ------------------------------------------------------------------------------------------------
@@ -135,6 +158,23 @@ def _panel(rng, n, Gs, C):
     codes = [rng.integers(0, g, n).astype(np.int32) for g in Gs]
     cols = [rng.normal(size=n) + sum(rng.normal(size=g)[c] for g, c in zip(Gs, codes)) for _ in range(C)]
     return cols, codes
+
+
+@pytest.mark.parametrize("Gs", [(1_000_000, 500), (500, 1_000_000), (70_000, 60_000), (5, 3), (1, 1), (2_000_000, 1),
+                                (40_000, 65_536)])
+def test_demean_two_fe_packed_entry_lists(eng, Gs):
+    # unweighted two-FE fits whose codes fit one 32-bit word together take the packed-word entry lists
+    rng = np.random.default_rng(17)
+    n = 400_003
+    cols, codes = _panel(rng, n, Gs, 3)
+    order = O.fe_order(list(Gs))
+    exp_cols, exp_it, exp_mm = O.alt_proj(cols, codes, order, 0.0, 6, None)
+    d_cols = [dev(c) for c in cols]
+    it, mm, conv = eng.demean(d_cols, [dev(c) for c in codes], list(Gs), order, None, 0.0, 6, 3)
+    assert it == exp_it == 6 and not conv
+    for got, exp in zip(d_cols, exp_cols):
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=2e-12)
+    assert mm == pytest.approx(exp_mm, rel=1e-6, abs=1e-14)
 
 
 @pytest.mark.parametrize("Gs,C,weighted", [((3000, 40), 3, False), ((3000, 40), 6, True), ((500, 200, 12), 2, False),
