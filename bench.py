@@ -270,13 +270,14 @@ def main():
     proj_launches = max(counters["sweep_launches"] / args.steps, 1)
     proj_ms = (timers["demean_sweeps"] + timers["demean_check"]) / args.steps / proj_launches
     sweep_ms = F * proj_ms
-    # bytes the coefficient-space sweep must move: per projection the FE-sorted int32 key + the other FE's code,
-    # plus one read of S0 and one read-modify-write of alpha/acc per group row (SURVEY 8d 'read-only sweep' form)
+    # bytes the coefficient-space sweep must move: per projection one packed 32-bit (unit code, time code) word
+    # per entry of the FE-sorted list, plus one read of S0 and one read-modify-write of alpha/acc per group row
+    # (SURVEY 8d 'read-only sweep' form)
     G_unit, G_time = n // ROWS_PER_UNIT, N_TIME
-    own_bytes = F * n * 4 * F + 5 * 8 * C * (G_unit + G_time)
+    own_bytes = F * n * 4 + 5 * 8 * C * (G_unit + G_time)
     inplace_bytes = n * F * (16 * C + 8)                    # the reference's in-place formulation
     roofline = {
-        "bound": "hbm", "kernel": "k_proj<6,false> + k_finalize (one sweep = 2 projections)",
+        "bound": "hbm", "kernel": "k_proj_q<6> (time FE) + k_proj<6> (unit FE) + k_finalize (one sweep = 2 projections)",
         "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak,
         # ncu dram__bytes_read+write of the two k_proj launches of one sweep at this exact config

@@ -127,6 +127,108 @@ __global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ ke
   }
 }
 
+// Packed two-FE projection whose other table lives in global memory (L2): lanes cooperate on the gathered rows.
+// In k_proj every lane gathers its own 8*NC-byte row with up to NC/2 128-bit loads, so a warp-wide load touches
+// 32 different cache lines and the kernel is bound by L1TEX wavefronts (87 % of peak at c2, ncu r1), one per
+// line, ~2.5 per entry.  Here a row group of LPR = 4 (NC <= 8), 2 (NC <= 4) or 1 lanes owns an entry: lane p
+// loads the 16-byte piece p of the row, so a warp-wide load covers 32 / LPR whole rows with ~1.3 lines per
+// entry, and owns columns 2p, 2p+1 of the running group sum.  A row group walks PQ_E * PQ_R consecutive
+// entries (words fetched 128-bit per lane and handed round with shuffles), folds equal keys in registers,
+// flushes finished runs with RED.ADD.F64, and the open runs of the 32 / LPR groups are merged by a segmented
+// shuffle scan before the last flush -- the same run-merging as k_proj, at quarter-warp granularity.
+constexpr int PQ_E = 16;   // entries per row group per round (one 128-bit word load per lane when LPR = 4)
+constexpr int PQ_R = 2;    // rounds per chunk: a row group owns 32 consecutive entries
+
+template <int NC>
+__global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__ words, const double* __restrict__ tab,
+                                                    int64_t n, int ldc, double* __restrict__ acc, int ld_acc,
+                                                    int acc_col0, PackSpec pk, bool vec2) {
+  constexpr int LPR = NC <= 2 ? 1 : (NC <= 4 ? 2 : 4);
+  constexpr int NG = 32 / LPR;
+  constexpr int WPL = PQ_E / LPR;            // entry words held by a lane per round
+  constexpr int GCH = PQ_E * PQ_R;           // entries per row group per chunk
+  constexpr int WCH = NG * GCH;              // entries per warp per chunk
+  const int lane = threadIdx.x & 31;
+  const int p = lane % LPR, g = lane / LPR;
+  const int c0 = 2 * p;
+  const bool has0 = c0 < NC, has1 = c0 + 1 < NC;
+  const bool pair = vec2 && has1;
+  const int64_t nchunk = ceil_div64(n, (int64_t)WCH);
+  const int64_t nwarps = (int64_t)gridDim.x * (PJ_T / 32);
+  for (int64_t ch = (int64_t)blockIdx.x * (PJ_T / 32) + (threadIdx.x >> 5); ch < nchunk; ch += nwarps) {
+    int cur = -1;
+    double r0 = 0.0, r1 = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < PQ_R; ++r) {
+      const int64_t ebase = ch * WCH + (int64_t)g * GCH + (int64_t)r * PQ_E;
+      uint32_t mine[WPL];
+#pragma unroll
+      for (int q = 0; q < WPL / 4; ++q) {
+        const int64_t i0 = ebase + (int64_t)p * WPL + 4 * q;
+        if (i0 + 3 < n) {
+          const uint4 t = __ldcs(reinterpret_cast<const uint4*>(words + i0));
+          mine[4 * q] = t.x; mine[4 * q + 1] = t.y; mine[4 * q + 2] = t.z; mine[4 * q + 3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mine[4 * q + e] = i0 + e < n ? __ldcs(words + i0 + e) : 0u;
+        }
+      }
+#pragma unroll
+      for (int h0 = 0; h0 < PQ_E; h0 += 8) {
+        int k[8];
+        double v0[8], v1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int sidx = h0 + e;
+          const uint32_t w = __shfl_sync(0xffffffffu, mine[sidx % WPL], g * LPR + sidx / WPL);
+          const bool valid = ebase + sidx < n;
+          k[e] = valid ? (int)((w >> pk.kshift) & pk.kmask) : -1;
+          const uint32_t o = valid ? ((w >> pk.oshift) & pk.omask) : 0u;
+          const double* row = tab + (size_t)o * ldc + c0;
+          v0[e] = 0.0; v1[e] = 0.0;
+          if (valid) {
+            if (pair) {
+              const double2 t = *reinterpret_cast<const double2*>(row);
+              v0[e] = t.x; v1[e] = t.y;
+            } else {
+              if (has0) v0[e] = row[0];
+              if (has1) v1[e] = row[1];
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (k[e] == cur) {
+            r0 += v0[e]; r1 += v1[e];
+          } else {
+            if (cur >= 0) {
+              double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
+              if (has0) atomicAdd(a, r0);
+              if (has1) atomicAdd(a + 1, r1);
+            }
+            cur = k[e]; r0 = v0[e]; r1 = v1[e];
+          }
+        }
+      }
+    }
+    // merge the open runs of adjacent row groups (same p): inclusive segmented scan over the groups
+    const int prv = __shfl_up_sync(0xffffffffu, cur, LPR);
+    const unsigned heads = __ballot_sync(0xffffffffu, g == 0 || prv != cur);
+    const int seg_start = (31 - __clz(heads & (0xffffffffu >> (31 - lane)))) / LPR;   // first group of my segment
+#pragma unroll
+    for (int d = 1; d < NG; d <<= 1) {
+      const double t0 = shfl_up_d(r0, d * LPR), t1 = shfl_up_d(r1, d * LPR);
+      if (g - d >= seg_start) { r0 += t0; r1 += t1; }
+    }
+    const int nxt = __shfl_down_sync(0xffffffffu, cur, LPR);
+    if (cur >= 0 && (g == NG - 1 || nxt != cur)) {
+      double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
+      if (has0) atomicAdd(a, r0);
+      if (has1) atomicAdd(a + 1, r1);
+    }
+  }
+}
+
 // acc[key][acc_col0 + c] += w * col_c[perm ? perm[e] : e]     (S0 tables; also sum of weights with NC=1)
 template <int NC, bool WEIGHTED>
 __global__ void __launch_bounds__(PJ_T) k_segsum(const int32_t* __restrict__ key, ColPtrs cols,
@@ -181,6 +283,85 @@ __global__ void __launch_bounds__(256) k_binsum_smem(const int32_t* __restrict__
   for (int i = threadIdx.x; i < G * NC; i += blockDim.x) {
     double v = bins[i];
     if (v != 0.0) atomicAdd(acc + (size_t)(i / NC) * ld_acc + acc_col0 + (i % NC), v);
+  }
+}
+
+// S0 of ALL fixed effects in one pass over the columns (they are read once instead of once per FE): every
+// thread takes PJ_I consecutive rows; an FE whose G x NC bins fit the CTA's shared memory accumulates there
+// (smem_off >= 0), the others take the run-merged RED path of k_segsum.
+struct S0Spec {
+  const int32_t* code[LFE_MAX_FE];
+  double* acc[LFE_MAX_FE];
+  int G[LFE_MAX_FE];
+  int smem_off[LFE_MAX_FE];   // offset (doubles) of the FE's bins in shared memory, -1 = RED into acc
+  int F;
+  int smem_doubles;
+};
+
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(PJ_T) k_s0_fused(S0Spec sp, ColPtrs cols, const double* __restrict__ w, int64_t n,
+                                                   int ld_acc, int acc_col0, bool vec) {
+  extern __shared__ double bins[];
+  for (int i = threadIdx.x; i < sp.smem_doubles; i += blockDim.x) bins[i] = 0.0;
+  __syncthreads();
+  const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
+    double v[PJ_I][NC];
+    if (vec && base + PJ_I <= n) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(cols.col[c] + base));
+        const double2 b = __ldcs(reinterpret_cast<const double2*>(cols.col[c] + base) + 1);
+        v[0][c] = a.x; v[1][c] = a.y; v[2][c] = b.x; v[3][c] = b.y;
+      }
+      if (WEIGHTED) {
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(w + base));
+        const double2 b = __ldcs(reinterpret_cast<const double2*>(w + base) + 1);
+        const double we[PJ_I] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int e = 0; e < PJ_I; ++e)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) v[e][c] *= we[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e) {
+        const bool valid = base + e < n;
+        const double we = WEIGHTED ? (valid ? __ldcs(w + base + e) : 0.0) : 1.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const double x = valid ? __ldcs(cols.col[c] + base + e) : 0.0;
+          v[e][c] = WEIGHTED ? x * we : x;
+        }
+      }
+    }
+    for (int j = 0; j < sp.F; ++j) {
+      int k[PJ_I];
+      load4_i32(sp.code[j], base, n, vec, k);
+      if (sp.smem_off[j] >= 0) {
+        double* b0 = bins + sp.smem_off[j];
+#pragma unroll
+        for (int e = 0; e < PJ_I; ++e) {
+          if (k[e] >= 0) {
+            double* b = b0 + (size_t)k[e] * NC;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) atomicAdd(b + c, v[e][c]);
+          }
+        }
+      } else {
+        segmented_flush<NC>(k, v, sp.acc[j], ld_acc, acc_col0);
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < sp.F; ++j) {
+    if (sp.smem_off[j] < 0) continue;
+    const double* b0 = bins + sp.smem_off[j];
+    for (int i = threadIdx.x; i < sp.G[j] * NC; i += blockDim.x) {
+      const double x = b0[i];
+      if (x != 0.0) atomicAdd(sp.acc[j] + (size_t)(i / NC) * ld_acc + acc_col0 + (i % NC), x);
+    }
   }
 }
 
@@ -270,9 +451,71 @@ __global__ void __launch_bounds__(256) k_apply(MutColPtrs cols, ApplyTabs T, int
   }
 }
 
+// Same, four consecutive rows per thread with 128-bit code / column accesses: the per-row chain code load ->
+// table gather -> store left k_apply 91 % long-scoreboard-stalled at half occupancy; four independent chains
+// per thread give the memory system 4x the requests in flight.  Needs 16-byte aligned columns and codes.
+template <int NC>
+__global__ void __launch_bounds__(256, 2) k_apply4(MutColPtrs cols, ApplyTabs T, int64_t n, int ldc, int col0) {
+  extern __shared__ double sm_tabs[];
+  const double* tabs[LFE_MAX_FE];
+  stage_tables(T, ldc, sm_tabs, tabs);
+  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  const int64_t n4 = n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
+    double s[4][NC];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) s[e][c] = 0.0;
+    for (int j = 0; j < T.n; ++j) {
+      const int4 k4 = __ldcs(reinterpret_cast<const int4*>(T.code[j]) + g);
+      const int k[4] = {k4.x, k4.y, k4.z, k4.w};
+      const double* tab = tabs[j] + col0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double* row = tab + (size_t)k[e] * ldc;
+        if (vec2) {
+#pragma unroll
+          for (int c = 0; c < NC / 2; ++c) {
+            const double2 t = *(reinterpret_cast<const double2*>(row) + c);
+            s[e][2 * c] += t.x;
+            s[e][2 * c + 1] += t.y;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) s[e][c] += row[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double2 a = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g);
+      const double2 b = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g + 1);
+      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g, make_double2(a.x - s[0][c], a.y - s[1][c]));
+      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g + 1, make_double2(b.x - s[2][c], b.y - s[3][c]));
+    }
+  }
+  // the last n % 4 rows
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    double s[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s[c] = 0.0;
+    for (int j = 0; j < T.n; ++j) {
+      const double* row = tabs[j] + (size_t)T.code[j][i] * ldc + col0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) s[c] += row[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cols.col[c][i] = cols.src[c][i] - s[c];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 struct FEState {
   int64_t G = 0;
   bool identity = false;
@@ -290,8 +533,6 @@ struct FEState {
   const double* S0u = nullptr;  // unweighted y sums
   int ld_s0u = 1;
 };
-
-static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // decide which tables are small enough to be staged in shared memory; returns the dynamic smem bytes
 static size_t plan_staging(ProjOthers& o, const int64_t* rows, int ldc) {
@@ -316,6 +557,26 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
   bool vec = aligned16(st.key);
   if (!st.packed)
     for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
+  if (st.packed && oth.n == 1 && oth.stage_rows[0] == 0 && n >= 4096) {
+    // the other FE's table is too large for shared memory: row-group cooperative gathers
+    const int64_t nch = ceil_div64(n, (int64_t)(PJ_T / 32) * 32 * PQ_E * PQ_R / 4);   // >= CTA chunks for any LPR
+    const int qb = launch_blocks(h, nch, 3);
+    const bool vec2 = ((ldc & 1) == 0) && ((col0 & 1) == 0) && aligned16(oth.alpha[0]);
+#define PQ_CASE(NC_)                                                                                            \
+  case NC_:                                                                                                     \
+    k_proj_q<NC_><<<qb, PJ_T, 0, s>>>((const uint32_t*)st.key, oth.alpha[0] + col0, n, ldc, acc, ld_acc, acc_col0, \
+                                      st.pk, vec2);                                                             \
+    break;
+    switch (nc) {
+      PQ_CASE(1) PQ_CASE(2) PQ_CASE(3) PQ_CASE(4) PQ_CASE(5) PQ_CASE(6) PQ_CASE(7) PQ_CASE(8)
+      default: LFE_THROW(LFE_ERR_ARG, "launch_proj: nc=%d", nc);
+    }
+#undef PQ_CASE
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    h->n_sweep_launches += 1;
+    return;
+  }
 #define PJ_CASE(NC_)                                                                                          \
   case NC_:                                                                                                   \
     if (st.packed)                                                                                            \
@@ -384,11 +645,59 @@ static void launch_groupsum(lfe_ctx* h, int nc, const int32_t* key, int64_t G, c
   }
 }
 
+// S0 of every FE for one column batch in a single pass over the columns (F >= 2)
+template <bool WEIGHTED>
+static void launch_s0_fused(lfe_ctx* h, int nc, const int32_t* const* codes, const int64_t* G, double* const* acc,
+                            int F, const ColPtrs& cols, const double* w, int64_t n, int ld_acc, int acc_col0,
+                            cudaStream_t s) {
+  if (n <= 0) return;
+  S0Spec sp;
+  sp.F = F;
+  sp.smem_doubles = 0;
+  bool vec = (w == nullptr) || aligned16(w);
+  for (int c = 0; c < nc; ++c) vec = vec && aligned16(cols.col[c]);
+  for (int j = 0; j < F; ++j) {
+    sp.code[j] = codes[j];
+    sp.acc[j] = acc[j];
+    sp.G[j] = (int)(G[j] < 0x7fffffff ? G[j] : 0x7fffffff);
+    vec = vec && aligned16(codes[j]);
+    if (G[j] * nc + sp.smem_doubles <= BINSUM_MAX_DOUBLES) {
+      sp.smem_off[j] = sp.smem_doubles;
+      sp.smem_doubles += (int)(G[j] * nc);
+    } else {
+      sp.smem_off[j] = -1;
+    }
+  }
+  const size_t smem = (size_t)sp.smem_doubles * sizeof(double);
+  const int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : 3);
+  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)PJ_T * PJ_I), per_sm);
+#define S0_CASE(NC_)                                                                                            \
+  case NC_:                                                                                                     \
+    if (smem > 48 * 1024)                                                                                       \
+      CUDA_CHECK(cudaFuncSetAttribute(k_s0_fused<NC_, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                              \
+    k_s0_fused<NC_, WEIGHTED><<<blocks, PJ_T, smem, s>>>(sp, cols, w, n, ld_acc, acc_col0, vec);               \
+    break;
+  switch (nc) {
+    S0_CASE(1) S0_CASE(2) S0_CASE(3) S0_CASE(4) S0_CASE(5) S0_CASE(6) S0_CASE(7) S0_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_s0_fused: nc=%d", nc);
+  }
+#undef S0_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
 static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const ApplyTabs& T, int64_t n, int ldc, int col0,
                          size_t smem, cudaStream_t s) {
-  int blocks = launch_blocks(h, ceil_div64(n, 256), smem > 0 ? 4 : 8);
-#define AP_CASE(NC_) \
-  case NC_: k_apply<NC_><<<blocks, 256, smem, s>>>(cols, T, n, ldc, col0); break;
+  bool vec = true;
+  for (int c = 0; c < nc; ++c) vec = vec && aligned16(cols.col[c]) && aligned16(cols.src[c]);
+  for (int j = 0; j < T.n; ++j) vec = vec && aligned16(T.code[j]);
+  int blocks = vec ? launch_blocks(h, ceil_div64(n, 256 * 4), 2) : launch_blocks(h, ceil_div64(n, 256), smem > 0 ? 4 : 8);
+#define AP_CASE(NC_)                                                              \
+  case NC_:                                                                       \
+    if (vec) k_apply4<NC_><<<blocks, 256, smem, s>>>(cols, T, n, ldc, col0);      \
+    else k_apply<NC_><<<blocks, 256, smem, s>>>(cols, T, n, ldc, col0);           \
+    break;
   switch (nc) {
     AP_CASE(1) AP_CASE(2) AP_CASE(3) AP_CASE(4) AP_CASE(5) AP_CASE(6) AP_CASE(7) AP_CASE(8)
     default: LFE_THROW(LFE_ERR_ARG, "launch_apply: nc=%d", nc);
@@ -592,14 +901,27 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       S.alpha.zero(); S.S0.zero(); S.acc.zero();
       S.acc_chk.alloc(S.G, s);
       S.acc_chk.zero();
-      // S0 (weighted sums of every column), column batches of <= PJ_MAXNC
-      for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
-        int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
-        ColPtrs cp;
-        for (int c = 0; c < nc; ++c) cp.col[c] = in[c0 + c];
-        if (weighted) launch_groupsum<true>(h, nc, codes[j], S.G, cp, weights, n, S.S0, C, c0, s);
-        else launch_groupsum<false>(h, nc, codes[j], S.G, cp, nullptr, n, S.S0, C, c0, s);
+    }
+    // S0 (weighted sums of every column), column batches of <= PJ_MAXNC; with several FEs one fused pass
+    // per batch fills every FE's table, so the columns are read once
+    for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
+      int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+      ColPtrs cp;
+      for (int c = 0; c < nc; ++c) cp.col[c] = in[c0 + c];
+      if (F >= 2) {
+        int64_t Gs[LFE_MAX_FE];
+        double* accs[LFE_MAX_FE];
+        for (int j = 0; j < F; ++j) { Gs[j] = st[j].G; accs[j] = st[j].S0; }
+        if (weighted) launch_s0_fused<true>(h, nc, codes, Gs, accs, F, cp, weights, n, C, c0, s);
+        else launch_s0_fused<false>(h, nc, codes, Gs, accs, F, cp, nullptr, n, C, c0, s);
+      } else {
+        if (weighted) launch_groupsum<true>(h, nc, codes[0], st[0].G, cp, weights, n, st[0].S0, C, c0, s);
+        else launch_groupsum<false>(h, nc, codes[0], st[0].G, cp, nullptr, n, st[0].S0, C, c0, s);
       }
+    }
+    for (int j = 0; j < F; ++j) {
+      FEState& S = st[j];
+      size_t tab = (size_t)S.G * C;
       if (weighted) {
         // unweighted y sums for the convergence check (polars_impl.py:513 ignores the weights)
         S.S0u_buf.alloc(S.G, s);
