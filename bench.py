@@ -280,9 +280,9 @@ def main():
         "bound": "hbm", "kernel": "k_proj_q<6> (time FE) + k_proj<6> (unit FE) + k_finalize (one sweep = 2 projections)",
         "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak,
-        # ncu dram__bytes_read+write of the two k_proj launches of one sweep at this exact config
-        # (profiles/r1_ncu_top_kernels.md); null at other sizes
-        "traffic": 0.92e9 if (n == 50_000_000 and world == 1) else None,
+        # ncu dram__bytes_read+write of the two projection launches of one sweep at this exact config
+        # (profiles/r1_ncu_top_kernels_s2.md: k_proj_q 0.260 GB + k_proj 0.266 GB); null at other sizes
+        "traffic": 0.526e9 if (n == 50_000_000 and world == 1) else None,
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
         "proj_launches_per_fit": proj_launches,
         "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
