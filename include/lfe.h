@@ -87,6 +87,15 @@ int lfe_factorize(lfe_handle h, const void* keys, int key_dtype, int64_t n, int 
                   int32_t* codes_out, int64_t* n_groups_out /*[host]*/,
                   void* uniques_out, int64_t uniques_cap, void* stream);
 
+/* Group sizes as a by-product of the LAST lfe_factorize call on this handle: when that call took the
+ * direct-address path (rank-local sorted-rank codes of keys with a small range -- panel ids) it counted
+ * occurrences instead of marking presence, so `len().over(fe)` (polars_impl.py:478-482) costs no extra pass.
+ * `codes` must be the codes_out pointer of that call and n_groups its result.  available_out [host] = 1 and
+ * counts_out[g] = #rows with code g when the counts exist, else 0 (use lfe_group_counts).  The handle's copy
+ * is released by this call.                                                                          */
+int lfe_factorize_counts(lfe_handle h, const int32_t* codes, int64_t n_groups, int32_t* counts_out,
+                         int* available_out /*[host]*/, void* stream);
+
 /* counts_out[g] = #rows with codes == g  (int32, length n_groups) */
 int lfe_group_counts(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_groups,
                      int32_t* counts_out, void* stream);

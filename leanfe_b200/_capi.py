@@ -24,7 +24,7 @@ ERR_CAPACITY = -3
 
 EXPORTS = [
     "lfe_version", "lfe_last_error", "lfe_create", "lfe_destroy", "lfe_set_profiling", "lfe_reset_timers",
-    "lfe_get_timers", "lfe_get_counters", "lfe_factorize", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
+    "lfe_get_timers", "lfe_get_counters", "lfe_factorize", "lfe_factorize_counts", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
     "lfe_sort_rows", "lfe_gather", "lfe_demean", "lfe_demean_plan_create", "lfe_demean_plan_run",
     "lfe_demean_plan_destroy", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
@@ -62,6 +62,7 @@ def load_library() -> C.CDLL:
     lib.lfe_get_timers.argtypes = [vp, P(dbl)]
     lib.lfe_get_counters.argtypes = [vp, P(i64)]
     lib.lfe_factorize.argtypes = [vp, vp, i32, i64, i32, vp, P(i64), vp, i64, vp]
+    lib.lfe_factorize_counts.argtypes = [vp, vp, i64, vp, P(i32), vp]
     lib.lfe_group_counts.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.lfe_singleton_mask.argtypes = [vp, P(vp), P(i64), i32, i64, i32, P(vp), vp, P(i64), P(i64), vp]
     lib.lfe_compact.argtypes = [vp, vp, i64, P(vp), P(vp), i32, P(vp), P(vp), i32, vp]

@@ -291,7 +291,8 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
         Gs = [f.n_groups for f in fe_keys]
         order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
         # singleton filter: one pass, all FEs (polars_impl.py:478-482)
-        counts = [eng.group_counts(c, g) for c, g in zip(codes, Gs)]       # shared by the filter and the plan
+        # group sizes, shared by the filter and the plan: a by-product of the factorisation when it counted
+        counts = [f.counts if f.counts is not None else eng.group_counts(f.codes, f.n_groups) for f in fe_keys]
         keep, n_keep, fe_dims = eng.singleton_mask(codes, Gs, local_fe, counts)
         n_obs = eng.last_n_keep_global
         if n_obs == 0:

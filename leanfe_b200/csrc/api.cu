@@ -190,6 +190,7 @@ int lfe_destroy(lfe_handle h) {
   drain_timers(h);
   for (auto e : h->free_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
+  h->last_counts.release();
   delete h;
   LFE_API_END
 }
@@ -234,6 +235,23 @@ int lfe_factorize(lfe_handle h, const void* keys, int key_dtype, int64_t n, int 
   *n_groups_out = G;
   if (uniques_out && G > uniques_cap)
     LFE_THROW(LFE_ERR_CAPACITY, "lfe_factorize: %lld groups exceed uniques_cap %lld", (long long)G, (long long)uniques_cap);
+  LFE_API_END
+}
+
+int lfe_factorize_counts(lfe_handle h, const int32_t* codes, int64_t n_groups, int32_t* counts_out,
+                         int* available_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && available_out, "lfe_factorize_counts: NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  *available_out = 0;
+  if (h->last_counts.p && h->last_counts_G == n_groups && h->last_counts_codes == (const void*)codes && counts_out) {
+    CUDA_CHECK(cudaMemcpyAsync(counts_out, h->last_counts.p, (size_t)n_groups * sizeof(int32_t),
+                               cudaMemcpyDeviceToDevice, S(stream)));
+    *available_out = 1;
+  }
+  h->last_counts.release();
+  h->last_counts_G = -1;
+  h->last_counts_codes = nullptr;
   LFE_API_END
 }
 

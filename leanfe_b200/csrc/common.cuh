@@ -64,6 +64,24 @@ struct lfe_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   int world_attached = 1;   // size of the attached communicator; world == 1 while collectives are suspended
+  // group sizes produced as a by-product of the last lfe_factorize call (direct-address path), see
+  // lfe_factorize_counts; owned by the handle, stream-ordered
+  struct CountsBuf {
+    uint32_t* p = nullptr;
+    cudaStream_t s = nullptr;
+    void alloc(size_t n, cudaStream_t s_) {
+      release();
+      s = s_;
+      if (n && cudaMallocAsync((void**)&p, n * sizeof(uint32_t), s) != cudaSuccess) p = nullptr;
+    }
+    void release() {
+      if (p) cudaFreeAsync(p, s);
+      p = nullptr;
+    }
+    operator uint32_t*() const { return p; }
+  } last_counts;
+  int64_t last_counts_G = -1;
+  const void* last_counts_codes = nullptr;
 };
 
 // RAII phase timer: records a CUDA-event pair on the stream when profiling is on.

@@ -139,13 +139,72 @@ __global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ ke
 constexpr int PQ_E = 16;   // entries per row group per round (one 128-bit word load per lane when LPR = 4)
 constexpr int PQ_R = 2;    // rounds per chunk: a row group owns 32 consecutive entries
 
+// one round of a row group: PQ_E entries folded into the open run (cur, r0, r1).  FULL: all entries exist.
+template <int NC, int LPR, bool FULL>
+__device__ __forceinline__ void quad_round(const uint32_t* __restrict__ words, const double* __restrict__ tab,
+                                           int64_t ebase, int64_t n, int ldc, const PackSpec& pk, bool pair, int p,
+                                           int g, int c0, double* __restrict__ acc, int ld_acc, int acc_col0,
+                                           int& cur, double& r0, double& r1) {
+  constexpr int WPL = PQ_E / LPR;            // entry words held by a lane per round
+  const bool has0 = c0 < NC, has1 = c0 + 1 < NC;
+  const int rem = FULL ? PQ_E : (int)(n - ebase < (int64_t)PQ_E ? n - ebase : (int64_t)PQ_E);   // may be <= 0
+  uint32_t mine[WPL];
+#pragma unroll
+  for (int q = 0; q < WPL / 4; ++q) {
+    const int off = p * WPL + 4 * q;
+    if (FULL || off + 3 < rem) {
+      const uint4 t = __ldcs(reinterpret_cast<const uint4*>(words + ebase + off));
+      mine[4 * q] = t.x; mine[4 * q + 1] = t.y; mine[4 * q + 2] = t.z; mine[4 * q + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mine[4 * q + e] = off + e < rem ? __ldcs(words + ebase + off + e) : 0u;
+    }
+  }
+#pragma unroll
+  for (int h0 = 0; h0 < PQ_E; h0 += 8) {
+    int k[8];
+    double v0[8], v1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int sidx = h0 + e;
+      const uint32_t w = __shfl_sync(0xffffffffu, mine[sidx % WPL], g * LPR + sidx / WPL);
+      const bool valid = FULL || sidx < rem;
+      k[e] = valid ? (int)((w >> pk.kshift) & pk.kmask) : -1;
+      const uint32_t o = valid ? ((w >> pk.oshift) & pk.omask) : 0u;
+      const double* row = tab + (size_t)o * ldc + c0;
+      v0[e] = 0.0; v1[e] = 0.0;
+      if (valid) {
+        if (pair) {
+          const double2 t = *reinterpret_cast<const double2*>(row);
+          v0[e] = t.x; v1[e] = t.y;
+        } else {
+          if (has0) v0[e] = row[0];
+          if (has1) v1[e] = row[1];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (k[e] == cur) {
+        r0 += v0[e]; r1 += v1[e];
+      } else {
+        if (cur >= 0) {
+          double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
+          if (has0) atomicAdd(a, r0);
+          if (has1) atomicAdd(a + 1, r1);
+        }
+        cur = k[e]; r0 = v0[e]; r1 = v1[e];
+      }
+    }
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__ words, const double* __restrict__ tab,
                                                     int64_t n, int ldc, double* __restrict__ acc, int ld_acc,
                                                     int acc_col0, PackSpec pk, bool vec2) {
   constexpr int LPR = NC <= 2 ? 1 : (NC <= 4 ? 2 : 4);
   constexpr int NG = 32 / LPR;
-  constexpr int WPL = PQ_E / LPR;            // entry words held by a lane per round
   constexpr int GCH = PQ_E * PQ_R;           // entries per row group per chunk
   constexpr int WCH = NG * GCH;              // entries per warp per chunk
   const int lane = threadIdx.x & 31;
@@ -158,58 +217,17 @@ __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__
   for (int64_t ch = (int64_t)blockIdx.x * (PJ_T / 32) + (threadIdx.x >> 5); ch < nchunk; ch += nwarps) {
     int cur = -1;
     double r0 = 0.0, r1 = 0.0;
+    const int64_t gbase = ch * WCH + (int64_t)g * GCH;
+    if ((ch + 1) * WCH <= n) {
 #pragma unroll 1
-    for (int r = 0; r < PQ_R; ++r) {
-      const int64_t ebase = ch * WCH + (int64_t)g * GCH + (int64_t)r * PQ_E;
-      uint32_t mine[WPL];
-#pragma unroll
-      for (int q = 0; q < WPL / 4; ++q) {
-        const int64_t i0 = ebase + (int64_t)p * WPL + 4 * q;
-        if (i0 + 3 < n) {
-          const uint4 t = __ldcs(reinterpret_cast<const uint4*>(words + i0));
-          mine[4 * q] = t.x; mine[4 * q + 1] = t.y; mine[4 * q + 2] = t.z; mine[4 * q + 3] = t.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) mine[4 * q + e] = i0 + e < n ? __ldcs(words + i0 + e) : 0u;
-        }
-      }
-#pragma unroll
-      for (int h0 = 0; h0 < PQ_E; h0 += 8) {
-        int k[8];
-        double v0[8], v1[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int sidx = h0 + e;
-          const uint32_t w = __shfl_sync(0xffffffffu, mine[sidx % WPL], g * LPR + sidx / WPL);
-          const bool valid = ebase + sidx < n;
-          k[e] = valid ? (int)((w >> pk.kshift) & pk.kmask) : -1;
-          const uint32_t o = valid ? ((w >> pk.oshift) & pk.omask) : 0u;
-          const double* row = tab + (size_t)o * ldc + c0;
-          v0[e] = 0.0; v1[e] = 0.0;
-          if (valid) {
-            if (pair) {
-              const double2 t = *reinterpret_cast<const double2*>(row);
-              v0[e] = t.x; v1[e] = t.y;
-            } else {
-              if (has0) v0[e] = row[0];
-              if (has1) v1[e] = row[1];
-            }
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (k[e] == cur) {
-            r0 += v0[e]; r1 += v1[e];
-          } else {
-            if (cur >= 0) {
-              double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
-              if (has0) atomicAdd(a, r0);
-              if (has1) atomicAdd(a + 1, r1);
-            }
-            cur = k[e]; r0 = v0[e]; r1 = v1[e];
-          }
-        }
-      }
+      for (int r = 0; r < PQ_R; ++r)
+        quad_round<NC, LPR, true>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, pair, p, g, c0, acc, ld_acc,
+                                  acc_col0, cur, r0, r1);
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < PQ_R; ++r)
+        quad_round<NC, LPR, false>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, pair, p, g, c0, acc, ld_acc,
+                                   acc_col0, cur, r0, r1);
     }
     // merge the open runs of adjacent row groups (same p): inclusive segmented scan over the groups
     const int prv = __shfl_up_sync(0xffffffffu, cur, LPR);

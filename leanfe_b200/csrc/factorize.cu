@@ -96,6 +96,54 @@ __global__ void __launch_bounds__(256) k_mark(const typename KeyIO<DT>::T* __res
   }
 }
 
+// Direct-address COUNT table instead of presence flags: cnt[key - kmin] += 1.  Presence, ranks and the group
+// sizes (which the singleton filter and the demean plan need next) all come from this one pass.
+// Large ranges: RED.ADD.U32 into the L2-resident table, warp-aggregated only when neighbouring lanes hold
+// equal keys (sorted panels); random ids have no duplicates inside a warp and MATCH.ANY would be pure latency.
+template <int DT>
+__global__ void __launch_bounds__(256) k_count_global(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                                      unsigned long long kmin, uint32_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = ceil_div64(n, stride);
+  for (int64_t r = 0; r < nround; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t c = valid ? (uint32_t)(KeyIO<DT>::enc(__ldcs(keys + i)) - kmin) : (0xffffff00u + lane);
+    const uint32_t nb = __shfl_down_sync(0xffffffffu, c, 1);
+    if (__any_sync(0xffffffffu, lane < 31 && nb == c)) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, c);
+      if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&cnt[c], (uint32_t)__popc(peers));
+    } else if (valid) {
+      atomicAdd(&cnt[c], 1u);
+    }
+  }
+}
+// Small ranges (<= 8192 distinct values possible): per-CTA bins in shared memory, native 32-bit shared atomics.
+template <int DT>
+__global__ void __launch_bounds__(256) k_count_smem(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
+                                                    unsigned long long kmin, int range, uint32_t* __restrict__ cnt) {
+  extern __shared__ uint32_t sh_cnt[];
+  for (int i = threadIdx.x; i < range; i += blockDim.x) sh_cnt[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh_cnt[(uint32_t)(KeyIO<DT>::enc(__ldcs(keys + i)) - kmin)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < range; i += blockDim.x)
+    if (sh_cnt[i]) atomicAdd(&cnt[i], sh_cnt[i]);
+}
+__global__ void __launch_bounds__(256) k_flags_from_counts(const uint32_t* __restrict__ cnt, int64_t range,
+                                                           uint32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = cnt[i] ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_compact_counts(const uint32_t* __restrict__ cnt,
+                                                        const uint32_t* __restrict__ rank, int64_t range,
+                                                        uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range; i += (int64_t)gridDim.x * blockDim.x)
+    if (cnt[i]) out[rank[i]] = cnt[i];
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) k_lookup(const typename KeyIO<DT>::T* __restrict__ keys, int64_t n,
                                                 unsigned long long kmin, const uint32_t* __restrict__ rank,
@@ -201,13 +249,30 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
     LFE_REQUIRE(span < (1ull << 28), "lfe_factorize: LFE_ORDER_GLOBAL needs a key range < 2^28 (got %llu)", span);
     direct_limit = 1ull << 28;
   }
+  h->last_counts.release();
+  h->last_counts_G = -1;
   if (span < direct_limit) {
     int64_t range = (int64_t)span + 1;
-    DevBuf<uint32_t> flags(range, s), rank(range, s);
-    flags.zero();
-    if (n > 0) {
-      k_mark<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, flags);
+    DevBuf<uint32_t> flags(range, s), rank(range, s), cnt;
+    // rank-local sorted-rank codes: count instead of mark, the group sizes are a by-product
+    const bool want_counts = !global && order == LFE_ORDER_SORTED && n > 0;
+    if (want_counts) {
+      cnt.alloc(range, s);
+      cnt.zero();
+      if (range <= 8192)
+        k_count_smem<DT><<<blocks, 256, (size_t)range * sizeof(uint32_t), s>>>(keys, n, kmin, (int)range, cnt);
+      else
+        k_count_global<DT><<<launch_blocks(h, ceil_div64(n, 256 * 8), 8), 256, 0, s>>>(keys, n, kmin, cnt);
       KERNEL_CHECK();
+      k_flags_from_counts<<<launch_blocks(h, ceil_div64(range, 256 * 4), 8), 256, 0, s>>>(cnt, range, flags);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    } else {
+      flags.zero();
+      if (n > 0) {
+        k_mark<DT><<<blocks, 256, 0, s>>>(keys, n, kmin, flags);
+        KERNEL_CHECK();
+      }
     }
     if (global) comm_allreduce_int(h, flags.p, range, 0, 2, s);
     prim_exclusive_scan_u32(h, flags, rank, range, total, s);
@@ -220,6 +285,14 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
     CUDA_CHECK(cudaStreamSynchronize(s));
     G = ht;
     h->n_launches += 2;
+    if (want_counts && G > 0) {
+      h->last_counts.alloc(G, s);
+      k_compact_counts<<<launch_blocks(h, ceil_div64(range, 256 * 4), 8), 256, 0, s>>>(cnt, rank, range, h->last_counts);
+      KERNEL_CHECK();
+      h->last_counts_G = G;
+      h->last_counts_codes = codes;
+      h->n_launches += 1;
+    }
     if (uniques && G <= uniques_cap) {
       int b2 = launch_blocks(h, ceil_div64(range, 256 * 4), 8);
       k_emit_uniques_direct<DT><<<b2, 256, 0, s>>>(flags, rank, range, kmin, uniques);

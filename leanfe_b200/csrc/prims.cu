@@ -148,8 +148,15 @@ __global__ void __launch_bounds__(256) k_hist_smem(const int32_t* __restrict__ c
     int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     uint32_t c = valid ? (uint32_t)__ldcs(codes + i) : (0x80000000u + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, c);
-    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&sh[c], __popc(peers));
+    // aggregate in the warp only when neighbouring lanes hold equal codes (sorted / clustered rows); for random
+    // codes MATCH.ANY finds nothing and costs more than the atomics it would save
+    const uint32_t nb = __shfl_down_sync(0xffffffffu, c, 1);
+    if (__any_sync(0xffffffffu, lane < 31 && nb == c)) {
+      uint32_t peers = __match_any_sync(0xffffffffu, c);
+      if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&sh[c], __popc(peers));
+    } else if (valid) {
+      atomicAdd(&sh[c], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < G; i += blockDim.x)
@@ -165,8 +172,13 @@ __global__ void __launch_bounds__(256) k_hist_global(const int32_t* __restrict__
     int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     uint32_t c = valid ? (uint32_t)__ldcs(codes + i) : (0x80000000u + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, c);
-    if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&counts[c], __popc(peers));
+    const uint32_t nb = __shfl_down_sync(0xffffffffu, c, 1);
+    if (__any_sync(0xffffffffu, lane < 31 && nb == c)) {
+      uint32_t peers = __match_any_sync(0xffffffffu, c);
+      if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&counts[c], __popc(peers));
+    } else if (valid) {
+      atomicAdd(&counts[c], 1u);
+    }
   }
 }
 

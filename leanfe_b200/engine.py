@@ -119,6 +119,16 @@ class Engine:
         capi.check(rc)
         return codes, int(G.value), (uniq[: G.value] if uniq is not None else None)
 
+    def factorize_counts(self, codes: torch.Tensor, n_groups: int) -> torch.Tensor | None:
+        """Group sizes left behind by the ``factorize`` call that produced ``codes`` (None when that call did not
+        take the counting path); must be asked for right after it."""
+        if n_groups <= 0:
+            return None
+        out = self.empty(n_groups, torch.int32)
+        ok = C.c_int(0)
+        capi.check(self.lib.lfe_factorize_counts(self.h, self._p(codes), n_groups, self._p(out), C.byref(ok), self.stream))
+        return out if ok.value else None
+
     def group_counts(self, codes: torch.Tensor, n_groups: int) -> torch.Tensor:
         self._check_dev(codes)
         out = self.empty(n_groups, torch.int32)

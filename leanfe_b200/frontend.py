@@ -142,6 +142,7 @@ class KeyColumn:
     codes: torch.Tensor
     n_groups: int
     labels: list | None = None     # python scalars in code order (sorted ascending)
+    counts: torch.Tensor | None = None   # int32 group sizes when the factorisation produced them for free
 
 
 def _is_stringlike(col) -> bool:
@@ -196,8 +197,9 @@ def to_device_key(eng: Engine, col, want_labels: bool = False, global_codes: boo
         t = t.to(torch.uint8)
     order = capi.ORDER_SORTED | (capi.ORDER_GLOBAL if global_codes else 0)
     codes, G, uniq = eng.factorize(t, order, want_uniques=want_labels, uniques_cap=1 << 16)
+    counts = eng.factorize_counts(codes, G)
     labels = uniq.cpu().tolist() if want_labels else None
-    return KeyColumn(codes, G, labels)
+    return KeyColumn(codes, G, labels, counts)
 
 
 def resolve_reference(labels: list, ref, var: str):

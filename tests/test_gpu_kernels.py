@@ -75,6 +75,32 @@ def test_factorize_integer_valued_doubles_take_the_direct_path(eng):
     np.testing.assert_array_equal(codes.cpu().numpy(), d.astype(np.int32))
 
 
+@pytest.mark.parametrize("kind", ["small_range", "large_range", "sorted", "gappy", "f64_integral"])
+def test_factorize_counts_by_product(eng, kind):
+    # the direct-address path counts occurrences instead of marking presence: group sizes come for free
+    rng = np.random.default_rng(23)
+    n = 300_011
+    if kind == "small_range":
+        a = rng.integers(-7, 490, n)
+    elif kind == "large_range":
+        a = rng.integers(10**9, 10**9 + 900_000, n)
+    elif kind == "sorted":
+        a = np.sort(rng.integers(0, 6_000, n))
+    elif kind == "gappy":
+        a = rng.integers(0, 40_000, n) * 3 + 5
+    else:
+        a = rng.integers(0, 20_000, n).astype(np.float64)
+    codes, G, _ = eng.factorize(dev(a))
+    counts = eng.factorize_counts(codes, G)
+    u, inv, cnt = np.unique(a, return_inverse=True, return_counts=True)
+    assert G == u.size
+    np.testing.assert_array_equal(codes.cpu().numpy(), inv)
+    assert counts is not None
+    np.testing.assert_array_equal(counts.cpu().numpy(), cnt)
+    assert eng.factorize_counts(codes, G) is None          # consumed: the handle keeps no copy
+    np.testing.assert_array_equal(eng.group_counts(codes, G).cpu().numpy(), cnt)
+
+
 def test_factorize_first_appearance(eng):
     rng = np.random.default_rng(3)
     v = rng.integers(0, 3000, 100_000) * 11 - 500
