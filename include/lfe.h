@@ -138,7 +138,9 @@ int lfe_gather(lfe_handle h, const int32_t* perm, int64_t n,
  * (weighted mean = sum(w c)/sum(w), :492-500).  n_groups[j] bounds codes[j]; empty groups are
  * allowed.  With a communicator attached (lfe_comm_init) rows are assumed sharded so that FE
  * `local_fe` (>= 0) has all rows of each of its groups on one rank; all other FE tables are
- * all-reduced once per projection.                                                              */
+ * all-reduced once per projection.  max_mean_out = the stopping quantity of the last test; when the fit
+ * stops unconverged with F >= 3 it is the first FE's group-mean maximum only (already >= tol, so the other
+ * FEs' y-only passes were skipped), i.e. a lower bound of the reference's quantity.               */
 #define LFE_DEMEAN_STRICT_CHECK 1 /* flags bit: stop on max |weighted group mean| over ALL columns < tol
                                     (true fixed point; used for the YOCO solve) instead of the reference test */
 int lfe_demean(lfe_handle h, double* const* cols, int C, const int32_t* const* codes,

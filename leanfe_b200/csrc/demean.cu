@@ -1023,17 +1023,8 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
     iterations = it;
     if (it >= min_iter && fast_check) {
       PhaseTimer t(h, s, 7);
+      // first FE of the order: its speculative projection is the stopping quantity for that FE
       dmax.zero();
-      for (int oi = 1; oi + 1 < F; ++oi) {   // middle FEs: explicit y-only group means
-        FEState& S = st[fe_order[oi]];
-        ProjOthers o = others_of(fe_order[oi], true);
-        launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
-        if (dist && fe_order[oi] != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
-        k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
-                                                                           S.G, C, dmax);
-        KERNEL_CHECK();
-        h->n_launches += 1;
-      }
       FEState& S1 = st[fe_order[0]];
       project(fe_order[0]);
       k_finalize<<<launch_blocks(h, ceil_div64(S1.G * C, 256), 8), 256, 0, s>>>(S1.alpha, alpha_next, S1.acc, S1.S0,
@@ -1043,6 +1034,27 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       if (dist) comm_allreduce(h, dmax, 1, 1, s);
       CUDA_CHECK(cudaMemcpyAsync(&max_mean, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
+      if (max_mean < tol && F > 2) {
+        // only now can the test pass: the middle FEs need explicit y-only group means.  (While the first FE
+        // alone is above tol the maximum over all FEs is too, so these passes are skipped -- a 3-way fit that
+        // runs to max_iter never pays for them; max_mean is then the first FE's value, a lower bound >= tol.)
+        dmax.zero();
+        for (int oi = 1; oi + 1 < F; ++oi) {
+          FEState& S = st[fe_order[oi]];
+          ProjOthers o = others_of(fe_order[oi], true);
+          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
+          if (dist && fe_order[oi] != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
+          k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
+                                                                             S.G, C, dmax);
+          KERNEL_CHECK();
+          h->n_launches += 1;
+        }
+        double mid = 0.0;
+        if (dist) comm_allreduce(h, dmax, 1, 1, s);
+        CUDA_CHECK(cudaMemcpyAsync(&mid, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (mid > max_mean) max_mean = mid;
+      }
       if (max_mean < tol) {
         converged = true;
         break;

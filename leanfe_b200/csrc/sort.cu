@@ -27,6 +27,7 @@ constexpr int RS_TILE = RS_T * RS_I;   // 8192 keys per tile
 constexpr int RS_WKEYS = 32 * RS_I;    // each warp owns 512 consecutive keys of the tile
 constexpr int RS_H = 8;                // ranking rounds whose ballots / atomics / shuffles are issued together
 
+// (MATCH.ANY instead of the ballots was measured again in this kernel: 50M-key passes got 0.13 ms slower.)
 // Lanes holding the same digit as this lane (the lane itself included), among valid lanes.  BITS ballots:
 // fixed cost, unlike MATCH.ANY whose latency grows with the number of distinct values in the warp -- and
 // with 9-11-bit digits of random codes nearly all 32 values are distinct.
