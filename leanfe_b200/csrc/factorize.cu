@@ -598,6 +598,16 @@ __global__ void __launch_bounds__(256) k_count_nonzero(const uint32_t* __restric
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
 }
 
+__global__ void __launch_bounds__(256) k_count_ones(const uint32_t* __restrict__ v, int64_t n,
+                                                    unsigned long long* __restrict__ out) {
+  unsigned int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    local += v[i] == 1u ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
 // Multi-GPU: group sizes of every FE except `local_fe` are summed over the ranks before the test; n_keep_out[0]
 // is the local, n_keep_out[1] the global number of kept rows; fe_dims are global.
 void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
@@ -622,7 +632,29 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
   DevBuf<unsigned long long> acc(2 + F, s);
   acc.zero();
   int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
-  if (n > 0) {
+  // No group of size one anywhere (the usual panel) => every row is kept: the row pass is skipped.  The group
+  // tables are G-sized, the row pass N-sized.  With several ranks the number of singleton groups is summed
+  // first so that all ranks take the same branch.
+  {
+    DevBuf<unsigned long long> ones(1, s);
+    ones.zero();
+    for (int j = 0; j < F; ++j) {
+      k_count_ones<<<launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8), 256, 0, s>>>(cnts[j], n_groups[j], ones);
+      KERNEL_CHECK();
+    }
+    h->n_launches += 1;
+    if (dist) comm_allreduce_int(h, ones.p, 1, 1, 0, s);
+    unsigned long long h_ones = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_ones, ones.p, sizeof(h_ones), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (h_ones == 0) {
+      if (n > 0) CUDA_CHECK(cudaMemsetAsync(keep, 1, (size_t)n, s));
+      unsigned long long hn[2] = {(unsigned long long)n, (unsigned long long)n};
+      CUDA_CHECK(cudaMemcpyAsync(acc.p, hn, sizeof(hn), cudaMemcpyHostToDevice, s));   // pageable: staged at once
+      blocks = 0;   // skip the row pass below
+    }
+  }
+  if (n > 0 && blocks > 0) {
     k_singleton_mask<<<blocks, 256, 0, s>>>(P, F, n, keep, acc);
     KERNEL_CHECK();
     h->n_launches += 1;
@@ -650,7 +682,7 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
       if (dropped) {  // a group survives iff it still has a kept row: one more pass over the codes
         CUDA_CHECK(cudaMemsetAsync(cnts[j].p, 0, (size_t)n_groups[j] * sizeof(uint32_t), s));
         if (n > 0) {
-          k_mark_kept_groups<<<blocks, 256, 0, s>>>(codes[j], keep, n, cnts[j]);
+          k_mark_kept_groups<<<launch_blocks(h, ceil_div64(n, 256 * 4), 8), 256, 0, s>>>(codes[j], keep, n, cnts[j]);
           KERNEL_CHECK();
           h->n_launches += 1;
         }

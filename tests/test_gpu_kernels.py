@@ -60,6 +60,17 @@ def test_factorize_float_keys_canonical(eng):
     assert not np.signbit(uniq.cpu().numpy()[exp_uniq == 0.0]).any()     # -0.0 was canonicalised to +0.0
 
 
+def test_factorize_float_keys_large_takes_the_64_bit_radix_sort(eng):
+    # 20M continuous doubles: 64-bit keys, 6 x 11-bit passes, 4 tiles per CTA and a ragged last CTA
+    rng = np.random.default_rng(29)
+    pool = rng.normal(size=700_000)
+    v = pool[rng.integers(0, pool.size, 20_000_003)]
+    codes, G, _ = eng.factorize(dev(v))
+    u, inv = np.unique(v, return_inverse=True)
+    assert G == u.size
+    np.testing.assert_array_equal(codes.cpu().numpy(), inv)
+
+
 def test_factorize_integer_valued_doubles_take_the_direct_path(eng):
     rng = np.random.default_rng(22)
     v = rng.integers(-3, 40, 120_000).astype(np.float64)
