@@ -247,6 +247,100 @@ __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__
   }
 }
 
+// Projection on a VERY low-cardinality FE j (G_j x NC <= PT_MAX_BINS doubles, e.g. 30 years x 3 columns) taken
+// while streaming the entry list of the BIG FE b instead of FE j's own list.  In j's own order every entry
+// gathers a row of b's table at random (c3: a 240 MB worker table walked 30 times from DRAM, 2.7 ms per
+// projection); in b's order that table is read once, sequentially (neighbouring lanes sit in neighbouring
+// groups of b, so a warp-wide row load touches a handful of lines), and the 30 x 3 sums live in THREAD-PRIVATE
+// shared-memory bins (layout [bin][thread]: conflict-free, no atomics), reduced per CTA at the end.
+constexpr int PT_T = 256;
+constexpr int PT_MAX_BINS = 96;   // doubles per thread: 96 x 256 x 8 B = 192 KB of shared memory per CTA
+
+// entries per thread per chunk: all code loads, then all table gathers of a chunk are issued back to back (the
+// kernel runs 8 warps per SM, so the memory parallelism has to come from inside the thread)
+template <int NC>
+struct TinyCfg { static constexpr int E = NC <= 3 ? 16 : (NC <= 6 ? 8 : 4); };
+
+template <int NC, bool WEIGHTED, bool PACKED>
+__global__ void __launch_bounds__(PT_T, 1) k_proj_tiny(const int32_t* __restrict__ key, const int32_t* __restrict__ code_j,
+                                                       ProjOthers oth, const double* __restrict__ tab_b,
+                                                       const double* __restrict__ w, int64_t n, int ldc, int col0,
+                                                       int Gj, double* __restrict__ acc, int ld_acc, int acc_col0,
+                                                       bool vec_codes, PackSpec pk) {
+  constexpr int E = TinyCfg<NC>::E;
+  extern __shared__ double priv[];   // [Gj * NC][PT_T]
+  const int nbins = Gj * NC;
+  for (int i = 0; i < nbins; ++i) priv[i * PT_T + threadIdx.x] = 0.0;   // thread-private: no barrier needed
+  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  const int64_t nchunk = ceil_div64(n, (int64_t)PT_T * E);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * PT_T + threadIdx.x) * E;
+    const bool full = base + E <= n;
+    int kb[E], kj[E];
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) load4_i32(key, base + 4 * q, n, vec_codes && full, kb + 4 * q);
+    if (PACKED) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint32_t word = (uint32_t)kb[e];
+        const bool valid = base + e < n;
+        kb[e] = valid ? (int)((word >> pk.kshift) & pk.kmask) : -1;
+        kj[e] = valid ? (int)((word >> pk.oshift) & pk.omask) : -1;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < E / 4; ++q) load4_i32(code_j, base + 4 * q, n, vec_codes && full, kj + 4 * q);
+    }
+    double v[E][NC];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double* row = tab_b + (size_t)(kb[e] >= 0 ? kb[e] : 0) * ldc + col0;
+      if (vec2) {
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) {
+          const double2 t = *(reinterpret_cast<const double2*>(row) + c);
+          v[e][2 * c] = t.x;
+          v[e][2 * c + 1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[e][c] = row[c];
+      }
+    }
+    for (int o = 0; o < oth.n; ++o) {
+      int oc[E];
+#pragma unroll
+      for (int q = 0; q < E / 4; ++q) load4_i32(oth.code[o], base + 4 * q, n, vec_codes && full, oc + 4 * q);
+      const double* tab = oth.alpha[o] + col0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const double* row = tab + (size_t)(oc[e] >= 0 ? oc[e] : 0) * ldc;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[e][c] += row[c];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (kj[e] >= 0) {
+        double we = 1.0;
+        if (WEIGHTED) we = __ldcs(w + base + e);
+        double* b = priv + (size_t)kj[e] * NC * PT_T + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) b[c * PT_T] += WEIGHTED ? v[e][c] * we : v[e][c];
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < nbins; i += PT_T / 32) {
+    double sum = 0.0;
+#pragma unroll
+    for (int t = lane; t < PT_T; t += 32) sum += priv[i * PT_T + t];
+    sum = warp_sum(sum);
+    if (lane == 0 && sum != 0.0) atomicAdd(acc + (size_t)(i / NC) * ld_acc + acc_col0 + (i % NC), sum);
+  }
+}
+
 // acc[key][acc_col0 + c] += w * col_c[perm ? perm[e] : e]     (S0 tables; also sum of weights with NC=1)
 template <int NC, bool WEIGHTED>
 __global__ void __launch_bounds__(PJ_T) k_segsum(const int32_t* __restrict__ key, ColPtrs cols,
@@ -614,6 +708,53 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
   h->n_sweep_launches += 1;
 }
 
+// projection on the tiny FE j over the entry list of the big FE b (see k_proj_tiny)
+template <bool WEIGHTED>
+static void launch_proj_tiny(lfe_ctx* h, int nc, const std::vector<FEState>& st, int b, int j, int F, int64_t n, int ldc,
+                             int col0, double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
+  const FEState& B = st[b];
+  ProjOthers o;
+  o.n = 0;
+  bool vec = aligned16(B.key);
+  if (!B.packed) {
+    vec = vec && aligned16(B.oth[j]);
+    for (int k = 0; k < F; ++k) {
+      if (k == b || k == j) continue;
+      o.code[o.n] = B.oth[k];
+      o.alpha[o.n] = st[k].alpha;
+      o.stage_rows[o.n] = 0;
+      vec = vec && aligned16(B.oth[k]);
+      o.n++;
+    }
+  }
+  const int Gj = (int)st[j].G;
+  const size_t smem = (size_t)Gj * nc * PT_T * sizeof(double);
+  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)PT_T * PJ_I), 1);
+#define PT_CASE(NC_)                                                                                                 \
+  case NC_:                                                                                                          \
+    if (B.packed) {                                                                                                  \
+      CUDA_CHECK(cudaFuncSetAttribute(k_proj_tiny<NC_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      PT_MAX_BINS * PT_T * (int)sizeof(double)));                                    \
+      k_proj_tiny<NC_, false, true><<<blocks, PT_T, smem, s>>>(B.key, nullptr, o, st[b].alpha, nullptr, n, ldc,     \
+                                                               col0, Gj, acc, ld_acc, acc_col0, vec, B.pk);          \
+    } else {                                                                                                         \
+      CUDA_CHECK(cudaFuncSetAttribute(k_proj_tiny<NC_, WEIGHTED, false>,                                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
+                                      PT_MAX_BINS * PT_T * (int)sizeof(double)));                                    \
+      k_proj_tiny<NC_, WEIGHTED, false><<<blocks, PT_T, smem, s>>>(B.key, B.oth[j], o, st[b].alpha, B.w, n, ldc,    \
+                                                                   col0, Gj, acc, ld_acc, acc_col0, vec, B.pk);      \
+    }                                                                                                                \
+    break;
+  switch (nc) {
+    PT_CASE(1) PT_CASE(2) PT_CASE(3) PT_CASE(4) PT_CASE(5) PT_CASE(6) PT_CASE(7) PT_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_proj_tiny: nc=%d", nc);
+  }
+#undef PT_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+  h->n_sweep_launches += 1;
+}
+
 template <bool WEIGHTED>
 static void launch_segsum(lfe_ctx* h, int nc, const int32_t* key, const ColPtrs& cols, const uint32_t* perm,
                           const double* w, int64_t n, double* acc, int ld_acc, int acc_col0, cudaStream_t s) {
@@ -733,6 +874,7 @@ struct lfe_plan {
   int64_t n = 0;
   bool weighted = false;
   int local_fe = -1;
+  int big = 0;   // highest-cardinality FE: its entry list was built first
   const int32_t* codes[LFE_MAX_FE] = {nullptr};
   const double* weights = nullptr;
   std::vector<FEState> st;
@@ -757,6 +899,7 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
     int big = 0;
     for (int j = 1; j < F; ++j)
       if (n_groups[j] > n_groups[big]) big = j;
+    plan->big = big;
     for (int j = 0; j < F; ++j) {
       st[j].G = n_groups[j];
       LFE_REQUIRE(st[j].G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
@@ -985,10 +1128,19 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
     FEState& S = st[j];
     if (F == 1) return;
     ProjOthers o = others_of(j, false);
+    // a very small FE is projected over the big FE's entry list with thread-private bins (k_proj_tiny)
+    const int big = plan->big;
+    const bool tiny = j != big && n >= 65536 && S.G * (C < PJ_MAXNC ? C : PJ_MAXNC) <= PT_MAX_BINS;
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
-      if (weighted) launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
-      else launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+      if (tiny) {
+        if (weighted) launch_proj_tiny<true>(h, nc, st, big, j, F, n, C, c0, S.acc, C, c0, s);
+        else launch_proj_tiny<false>(h, nc, st, big, j, F, n, C, c0, S.acc, C, c0, s);
+      } else if (weighted) {
+        launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+      } else {
+        launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+      }
     }
     if (dist && j != local_fe) {
       PhaseTimer tc(h, s, 13);

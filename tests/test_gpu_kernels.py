@@ -211,6 +211,27 @@ def test_demean_two_fe_packed_entry_lists(eng, Gs):
     assert it == exp_it == 6 and not conv
     for got, exp in zip(d_cols, exp_cols):
         np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=2e-12)
+    # (1, 1): the group mean of a constant FE after the sweep is pure summation noise, ~1e-13 either way
+    assert mm == pytest.approx(exp_mm, rel=1e-6, abs=1e-12)
+
+
+@pytest.mark.parametrize("Gs,C,weighted", [((200_000, 5_000, 30), 3, False), ((200_000, 5_000, 30), 3, True),
+                                           ((100_000, 12), 6, False), ((30, 150_000), 2, True),
+                                           ((40_000, 9, 4, 2), 5, False)])
+def test_demean_tiny_fe_projected_over_the_big_list(eng, Gs, C, weighted):
+    # FEs with G x C <= 96 are projected while streaming the big FE's entry list (thread-private bins)
+    rng = np.random.default_rng(31)
+    n = 400_003
+    cols, codes = _panel(rng, n, Gs, C)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    order = O.fe_order(list(Gs))
+    exp_cols, exp_it, exp_mm = O.alt_proj(cols, codes, order, 0.0, 5, w)
+    d_cols = [dev(c) for c in cols]
+    it, mm, conv = eng.demean(d_cols, [dev(c) for c in codes], list(Gs), order, dev(w) if weighted else None,
+                              0.0, 5, 3)
+    assert it == exp_it == 5 and not conv
+    for got, exp in zip(d_cols, exp_cols):
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=0, atol=2e-12)
     assert mm == pytest.approx(exp_mm, rel=1e-6, abs=1e-14)
 
 
