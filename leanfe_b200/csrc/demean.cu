@@ -140,13 +140,14 @@ constexpr int PQ_E = 16;   // entries per row group per round (one 128-bit word 
 constexpr int PQ_R = 2;    // rounds per chunk: a row group owns 32 consecutive entries
 
 // one round of a row group: PQ_E entries folded into the open run (cur, r0, r1).  FULL: all entries exist.
-template <int NC, int LPR, bool FULL>
+// VEC: table rows are 16-byte aligned (a lane that owns two columns loads them as one double2).
+template <int NC, int LPR, bool FULL, bool VEC>
 __device__ __forceinline__ void quad_round(const uint32_t* __restrict__ words, const double* __restrict__ tab,
-                                           int64_t ebase, int64_t n, int ldc, const PackSpec& pk, bool pair, int p,
+                                           int64_t ebase, int64_t n, int ldc, const PackSpec& pk, int p,
                                            int g, int c0, double* __restrict__ acc, int ld_acc, int acc_col0,
                                            int& cur, double& r0, double& r1) {
   constexpr int WPL = PQ_E / LPR;            // entry words held by a lane per round
-  const bool has0 = c0 < NC, has1 = c0 + 1 < NC;
+  const int ncl = NC - c0 >= 2 ? 2 : (NC - c0 == 1 ? 1 : 0);   // columns this lane owns
   const int rem = FULL ? PQ_E : (int)(n - ebase < (int64_t)PQ_E ? n - ebase : (int64_t)PQ_E);   // may be <= 0
   uint32_t mine[WPL];
 #pragma unroll
@@ -164,45 +165,51 @@ __device__ __forceinline__ void quad_round(const uint32_t* __restrict__ words, c
   for (int h0 = 0; h0 < PQ_E; h0 += 8) {
     int k[8];
     double v0[8], v1[8];
+    bool same = true;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int sidx = h0 + e;
       const uint32_t w = __shfl_sync(0xffffffffu, mine[sidx % WPL], g * LPR + sidx / WPL);
       const bool valid = FULL || sidx < rem;
       k[e] = valid ? (int)((w >> pk.kshift) & pk.kmask) : -1;
+      same = same && (k[e] == cur);
       const uint32_t o = valid ? ((w >> pk.oshift) & pk.omask) : 0u;
       const double* row = tab + (size_t)o * ldc + c0;
-      v0[e] = 0.0; v1[e] = 0.0;
-      if (valid) {
-        if (pair) {
-          const double2 t = *reinterpret_cast<const double2*>(row);
-          v0[e] = t.x; v1[e] = t.y;
-        } else {
-          if (has0) v0[e] = row[0];
-          if (has1) v1[e] = row[1];
-        }
+      if (VEC) {
+        double2 t = make_double2(0.0, 0.0);
+        if (valid && ncl == 2) t = *reinterpret_cast<const double2*>(row);
+        else if (valid && ncl == 1) t.x = row[0];
+        v0[e] = t.x; v1[e] = t.y;
+      } else {
+        v0[e] = (valid && ncl >= 1) ? row[0] : 0.0;
+        v1[e] = (valid && ncl == 2) ? row[1] : 0.0;
       }
     }
+    if (same) {   // the usual case inside a long group: no run ends here
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (k[e] == cur) {
-        r0 += v0[e]; r1 += v1[e];
-      } else {
-        if (cur >= 0) {
-          double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
-          if (has0) atomicAdd(a, r0);
-          if (has1) atomicAdd(a + 1, r1);
+      for (int e = 0; e < 8; ++e) { r0 += v0[e]; r1 += v1[e]; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (k[e] == cur) {
+          r0 += v0[e]; r1 += v1[e];
+        } else {
+          if (cur >= 0) {
+            double* a = acc + (size_t)cur * ld_acc + acc_col0 + c0;
+            if (ncl >= 1) atomicAdd(a, r0);
+            if (ncl == 2) atomicAdd(a + 1, r1);
+          }
+          cur = k[e]; r0 = v0[e]; r1 = v1[e];
         }
-        cur = k[e]; r0 = v0[e]; r1 = v1[e];
       }
     }
   }
 }
 
-template <int NC>
+template <int NC, bool VEC>
 __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__ words, const double* __restrict__ tab,
                                                     int64_t n, int ldc, double* __restrict__ acc, int ld_acc,
-                                                    int acc_col0, PackSpec pk, bool vec2) {
+                                                    int acc_col0, PackSpec pk) {
   constexpr int LPR = NC <= 2 ? 1 : (NC <= 4 ? 2 : 4);
   constexpr int NG = 32 / LPR;
   constexpr int GCH = PQ_E * PQ_R;           // entries per row group per chunk
@@ -211,7 +218,6 @@ __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__
   const int p = lane % LPR, g = lane / LPR;
   const int c0 = 2 * p;
   const bool has0 = c0 < NC, has1 = c0 + 1 < NC;
-  const bool pair = vec2 && has1;
   const int64_t nchunk = ceil_div64(n, (int64_t)WCH);
   const int64_t nwarps = (int64_t)gridDim.x * (PJ_T / 32);
   for (int64_t ch = (int64_t)blockIdx.x * (PJ_T / 32) + (threadIdx.x >> 5); ch < nchunk; ch += nwarps) {
@@ -221,13 +227,13 @@ __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__
     if ((ch + 1) * WCH <= n) {
 #pragma unroll 1
       for (int r = 0; r < PQ_R; ++r)
-        quad_round<NC, LPR, true>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, pair, p, g, c0, acc, ld_acc,
-                                  acc_col0, cur, r0, r1);
+        quad_round<NC, LPR, true, VEC>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, p, g, c0, acc, ld_acc,
+                                       acc_col0, cur, r0, r1);
     } else {
 #pragma unroll 1
       for (int r = 0; r < PQ_R; ++r)
-        quad_round<NC, LPR, false>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, pair, p, g, c0, acc, ld_acc,
-                                   acc_col0, cur, r0, r1);
+        quad_round<NC, LPR, false, VEC>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, p, g, c0, acc, ld_acc,
+                                        acc_col0, cur, r0, r1);
     }
     // merge the open runs of adjacent row groups (same p): inclusive segmented scan over the groups
     const int prv = __shfl_up_sync(0xffffffffu, cur, LPR);
@@ -676,8 +682,12 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
     const bool vec2 = ((ldc & 1) == 0) && ((col0 & 1) == 0) && aligned16(oth.alpha[0]);
 #define PQ_CASE(NC_)                                                                                            \
   case NC_:                                                                                                     \
-    k_proj_q<NC_><<<qb, PJ_T, 0, s>>>((const uint32_t*)st.key, oth.alpha[0] + col0, n, ldc, acc, ld_acc, acc_col0, \
-                                      st.pk, vec2);                                                             \
+    if (vec2)                                                                                                   \
+      k_proj_q<NC_, true><<<qb, PJ_T, 0, s>>>((const uint32_t*)st.key, oth.alpha[0] + col0, n, ldc, acc, ld_acc, \
+                                              acc_col0, st.pk);                                                 \
+    else                                                                                                        \
+      k_proj_q<NC_, false><<<qb, PJ_T, 0, s>>>((const uint32_t*)st.key, oth.alpha[0] + col0, n, ldc, acc, ld_acc, \
+                                               acc_col0, st.pk);                                                \
     break;
     switch (nc) {
       PQ_CASE(1) PQ_CASE(2) PQ_CASE(3) PQ_CASE(4) PQ_CASE(5) PQ_CASE(6) PQ_CASE(7) PQ_CASE(8)

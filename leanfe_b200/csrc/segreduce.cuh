@@ -52,6 +52,16 @@ __device__ __forceinline__ void load4_i32(const int32_t* __restrict__ p, int64_t
 template <int NC>
 __device__ __forceinline__ void run_fold(int& cur, double run[NC], const int key[PJ_I], double v[PJ_I][NC],
                                          double* __restrict__ acc, int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
+  bool same = true;
+#pragma unroll
+  for (int e = 0; e < PJ_I; ++e) same = same && (key[e] == cur);
+  if (same) {   // inside a long group of a sorted list no run ends here: straight-line adds
+#pragma unroll
+    for (int e = 0; e < PJ_I; ++e)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) run[c] += v[e][c];
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < PJ_I; ++e) {
     if (key[e] == cur) {
