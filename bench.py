@@ -228,7 +228,20 @@ def main():
 
     # ---- end-to-end arm: pinned host buffers -> public API -> result on the host ------------------
     e2e_s = float("nan")
+    h2d_only_ms = None
     if not args.no_e2e:
+        # the PCIe floor of the end-to-end arm: the same host tensors copied to the device with no compute
+        dst = {k_: torch.empty_like(t, device=dev) for k_, t in host.items()}
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            for k_, t in host.items():
+                dst[k_].copy_(t, non_blocking=True)
+        c1.record()
+        barrier()
+        h2d_only_ms = c0.elapsed_time(c1) / 3
+        del dst
         for _ in range(max(1, min(args.warmup, 2))):
             leanfe(host, **kw)
         barrier()
@@ -283,6 +296,8 @@ def main():
         # ncu dram__bytes_read+write of the two projection launches of one sweep at this exact config
         # (profiles/r1_ncu_top_kernels_s2.md: k_proj_q 0.260 GB + k_proj 0.266 GB); null at other sizes
         "traffic": 0.526e9 if (n == 50_000_000 and world == 1) else None,
+        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (84 % / 61 % of peak, "
+                   "profiles/r1_ncu_top_kernels_s2.md); the sweep reads only the packed code words",
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
         "proj_launches_per_fit": proj_launches,
         "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
@@ -300,7 +315,9 @@ def main():
                    "l2": "inputs (3.2 GB/GPU) exceed the 126 MB L2; no explicit flush", "tol": 1e-6,
                    "parallelism": f"row-sharded by unit x{world}" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * (2 * K_REG + 3),
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                # the same 3.2 GB copied host -> device with nothing else running: what PCIe alone costs per step
+                "h2d_only_ms_per_step": h2d_only_ms},
         "gpu_launches": int(counters["launches"]),
         "clocks": clocks, "roofline": roofline, "phases_ms_per_step": phases,
         "coefs": {k_: float(v) for k_, v in res.coefs.items()},

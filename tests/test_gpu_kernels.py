@@ -217,7 +217,8 @@ def test_demean_two_fe_packed_entry_lists(eng, Gs):
 
 @pytest.mark.parametrize("Gs,C,weighted", [((200_000, 5_000, 30), 3, False), ((200_000, 5_000, 30), 3, True),
                                            ((100_000, 12), 6, False), ((30, 150_000), 2, True),
-                                           ((40_000, 9, 4, 2), 5, False)])
+                                           ((40_000, 9, 4, 2), 5, False), ((60_000, 12), 8, False),
+                                           ((60_000, 12), 11, False)])
 def test_demean_tiny_fe_projected_over_the_big_list(eng, Gs, C, weighted):
     # FEs with G x C <= 96 are projected while streaming the big FE's entry list (thread-private bins)
     rng = np.random.default_rng(31)
