@@ -418,10 +418,13 @@ struct S0Spec {
 
 template <int NC, bool WEIGHTED>
 __global__ void __launch_bounds__(PJ_T) k_s0_fused(S0Spec sp, ColPtrs cols, const double* __restrict__ w, int64_t n,
-                                                   int ld_acc, int acc_col0, bool vec) {
-  extern __shared__ double bins[];
+                                                   int ld_acc, int acc_col0, bool vec, bool bulk) {
+  extern __shared__ __align__(16) double bins[];
   for (int i = threadIdx.x; i < sp.smem_doubles; i += blockDim.x) bins[i] = 0.0;
   __syncthreads();
+  // bulk: rows of the big tables go out as one TMA reduce each (see bulk_add_row); slots follow the bins
+  double* my_slots = bins + ((sp.smem_doubles + 1) & ~1) + (size_t)threadIdx.x * BulkRow<NC>::SLOT_DOUBLES;
+  int slot = 0;
   const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
     const int64_t base = (ch * PJ_T + threadIdx.x) * PJ_I;
@@ -467,11 +470,16 @@ __global__ void __launch_bounds__(PJ_T) k_s0_fused(S0Spec sp, ColPtrs cols, cons
             for (int c = 0; c < NC; ++c) atomicAdd(b + c, v[e][c]);
           }
         }
+      } else if (bulk && warp_keys_all_distinct_neighbours(k)) {
+#pragma unroll
+        for (int e = 0; e < PJ_I; ++e)
+          if (k[e] >= 0) bulk_add_row<NC>(sp.acc[j] + (size_t)k[e] * ld_acc + acc_col0, v[e], my_slots, slot);
       } else {
         segmented_flush<NC>(k, v, sp.acc[j], ld_acc, acc_col0);
       }
     }
   }
+  if (bulk) bulk_add_drain();
   __syncthreads();
   for (int j = 0; j < sp.F; ++j) {
     if (sp.smem_off[j] < 0) continue;
@@ -837,15 +845,22 @@ static void launch_s0_fused(lfe_ctx* h, int nc, const int32_t* const* codes, con
       sp.smem_off[j] = -1;
     }
   }
-  const size_t smem = (size_t)sp.smem_doubles * sizeof(double);
-  const int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : 3);
+  // TMA bulk reduce for the rows of the big tables: needs 16-byte aligned table rows (even ld / column offset)
+  bool bulk = (ld_acc % 2 == 0) && (acc_col0 % 2 == 0);
+  bool any_red = false;
+  for (int j = 0; j < F; ++j)
+    if (sp.smem_off[j] < 0) { any_red = true; bulk = bulk && aligned16(acc[j]); }
+  bulk = bulk && any_red;
+  const size_t slot_bytes = bulk ? (size_t)PJ_T * BR_SLOTS * ((nc + 1) & ~1) * sizeof(double) : 0;
+  const size_t smem = (size_t)((sp.smem_doubles + 1) & ~1) * sizeof(double) + slot_bytes;
+  const int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : (smem <= 72 * 1024 ? 3 : 2));
   const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)PJ_T * PJ_I), per_sm);
 #define S0_CASE(NC_)                                                                                            \
   case NC_:                                                                                                     \
     if (smem > 48 * 1024)                                                                                       \
       CUDA_CHECK(cudaFuncSetAttribute(k_s0_fused<NC_, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                              \
-    k_s0_fused<NC_, WEIGHTED><<<blocks, PJ_T, smem, s>>>(sp, cols, w, n, ld_acc, acc_col0, vec);               \
+    k_s0_fused<NC_, WEIGHTED><<<blocks, PJ_T, smem, s>>>(sp, cols, w, n, ld_acc, acc_col0, vec, bulk);         \
     break;
   switch (nc) {
     S0_CASE(1) S0_CASE(2) S0_CASE(3) S0_CASE(4) S0_CASE(5) S0_CASE(6) S0_CASE(7) S0_CASE(8)
@@ -1043,6 +1058,9 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
   const int32_t* const* codes = plan->codes;
   std::vector<FEState>& st = plan->st;
   LFE_REQUIRE(C >= 1, "lfe_demean: C must be >= 1");
+  // leading dimension of every FE table: C rounded up to even, so table rows are 16-byte aligned (128-bit
+  // gathers, TMA bulk reduces); the pad column stays zero throughout
+  const int Cp = (C + 1) & ~1;
   LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
   {
     bool seen[LFE_MAX_FE] = {false};
@@ -1067,7 +1085,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
     PhaseTimer t(h, s, 5);
     for (int j = 0; j < F; ++j) {
       FEState& S = st[j];
-      size_t tab = (size_t)S.G * C;
+      size_t tab = (size_t)S.G * Cp;
       S.alpha.alloc(tab, s); S.S0.alloc(tab, s); S.acc.alloc(tab, s);
       S.alpha.zero(); S.S0.zero(); S.acc.zero();
       S.acc_chk.alloc(S.G, s);
@@ -1083,16 +1101,16 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
         int64_t Gs[LFE_MAX_FE];
         double* accs[LFE_MAX_FE];
         for (int j = 0; j < F; ++j) { Gs[j] = st[j].G; accs[j] = st[j].S0; }
-        if (weighted) launch_s0_fused<true>(h, nc, codes, Gs, accs, F, cp, weights, n, C, c0, s);
-        else launch_s0_fused<false>(h, nc, codes, Gs, accs, F, cp, nullptr, n, C, c0, s);
+        if (weighted) launch_s0_fused<true>(h, nc, codes, Gs, accs, F, cp, weights, n, Cp, c0, s);
+        else launch_s0_fused<false>(h, nc, codes, Gs, accs, F, cp, nullptr, n, Cp, c0, s);
       } else {
-        if (weighted) launch_groupsum<true>(h, nc, codes[0], st[0].G, cp, weights, n, st[0].S0, C, c0, s);
-        else launch_groupsum<false>(h, nc, codes[0], st[0].G, cp, nullptr, n, st[0].S0, C, c0, s);
+        if (weighted) launch_groupsum<true>(h, nc, codes[0], st[0].G, cp, weights, n, st[0].S0, Cp, c0, s);
+        else launch_groupsum<false>(h, nc, codes[0], st[0].G, cp, nullptr, n, st[0].S0, Cp, c0, s);
       }
     }
     for (int j = 0; j < F; ++j) {
       FEState& S = st[j];
-      size_t tab = (size_t)S.G * C;
+      size_t tab = (size_t)S.G * Cp;
       if (weighted) {
         // unweighted y sums for the convergence check (polars_impl.py:513 ignores the weights)
         S.S0u_buf.alloc(S.G, s);
@@ -1101,7 +1119,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
         launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
         S.S0u = S.S0u_buf; S.ld_s0u = 1;
       } else {
-        S.S0u = S.S0; S.ld_s0u = C;
+        S.S0u = S.S0; S.ld_s0u = Cp;
       }
       if (dist && j != local_fe) {
         PhaseTimer tc(h, s, 13);
@@ -1124,7 +1142,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       o.n++;
     }
     (void)include_all_for_check;
-    proj_smem = plan_staging(o, rows, C);
+    proj_smem = plan_staging(o, rows, Cp);
     return o;
   };
 
@@ -1144,17 +1162,17 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
       if (tiny) {
-        if (weighted) launch_proj_tiny<true>(h, nc, st, big, j, F, n, C, c0, S.acc, C, c0, s);
-        else launch_proj_tiny<false>(h, nc, st, big, j, F, n, C, c0, S.acc, C, c0, s);
+        if (weighted) launch_proj_tiny<true>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
+        else launch_proj_tiny<false>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
       } else if (weighted) {
-        launch_proj<true>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+        launch_proj<true>(h, nc, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
       } else {
-        launch_proj<false>(h, nc, S, o, n, C, c0, S.acc, C, c0, proj_smem, s);
+        launch_proj<false>(h, nc, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
       }
     }
     if (dist && j != local_fe) {
       PhaseTimer tc(h, s, 13);
-      comm_allreduce(h, S.acc, S.G * C, 0, s);
+      comm_allreduce(h, S.acc, S.G * Cp, 0, s);
     }
   };
   // Unweighted fits: the reference's stopping quantity for the FIRST FE of the sweep order,
@@ -1164,7 +1182,7 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
   // coefficient space; only the middle FEs (F >= 3) need a y-only pass.
   const bool fast_check = !weighted && !strict_check && F >= 2 && tol > 1e-13;
   DevBuf<double> alpha_next;
-  if (fast_check) alpha_next.alloc((size_t)st[fe_order[0]].G * C, s);
+  if (fast_check) alpha_next.alloc((size_t)st[fe_order[0]].G * Cp, s);
   bool first_done = false;   // sweep it+1's first projection was already applied by the check of sweep it
 
   for (int it = 1; it <= max_iter; ++it) {
@@ -1175,8 +1193,8 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
         int j = fe_order[oi];
         FEState& S = st[j];
         project(j);
-        k_finalize<<<launch_blocks(h, ceil_div64(S.G * C, 256), 8), 256, 0, s>>>(
-            S.alpha, S.alpha, S.acc, S.S0, S.nsum, S.G, C, strict_check ? dmax.p : nullptr, -1);
+        k_finalize<<<launch_blocks(h, ceil_div64(S.G * Cp, 256), 8), 256, 0, s>>>(
+            S.alpha, S.alpha, S.acc, S.S0, S.nsum, S.G, Cp, strict_check ? dmax.p : nullptr, -1);
         KERNEL_CHECK();
         h->n_launches += 1;
       }
@@ -1189,8 +1207,8 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       dmax.zero();
       FEState& S1 = st[fe_order[0]];
       project(fe_order[0]);
-      k_finalize<<<launch_blocks(h, ceil_div64(S1.G * C, 256), 8), 256, 0, s>>>(S1.alpha, alpha_next, S1.acc, S1.S0,
-                                                                                  S1.nsum, S1.G, C, dmax, 0);
+      k_finalize<<<launch_blocks(h, ceil_div64(S1.G * Cp, 256), 8), 256, 0, s>>>(S1.alpha, alpha_next, S1.acc, S1.S0,
+                                                                                  S1.nsum, S1.G, Cp, dmax, 0);
       KERNEL_CHECK();
       h->n_launches += 1;
       if (dist) comm_allreduce(h, dmax, 1, 1, s);
@@ -1204,10 +1222,10 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
         for (int oi = 1; oi + 1 < F; ++oi) {
           FEState& S = st[fe_order[oi]];
           ProjOthers o = others_of(fe_order[oi], true);
-          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
+          launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
           if (dist && fe_order[oi] != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
           k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
-                                                                             S.G, C, dmax);
+                                                                             S.G, Cp, dmax);
           KERNEL_CHECK();
           h->n_launches += 1;
         }
@@ -1242,11 +1260,11 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
         FEState& S = st[j];
         if (F > 1) {
           ProjOthers o = others_of(j, true);
-          launch_proj<false>(h, 1, S, o, n, C, 0, S.acc_chk, 1, 0, proj_smem, s);
+          launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
           if (dist && j != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
         }
         k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
-                                                                           S.G, C, dmax);
+                                                                           S.G, Cp, dmax);
         KERNEL_CHECK();
         h->n_launches += 1;
       }
@@ -1271,12 +1289,12 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       T.alpha[j] = st[j].alpha;
       rows[j] = st[j].G;
     }
-    const size_t apply_smem = plan_staging(T, rows, C);
+    const size_t apply_smem = plan_staging(T, rows, Cp);
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
       MutColPtrs mp;
       for (int c = 0; c < nc; ++c) { mp.col[c] = cols[c0 + c]; mp.src[c] = in[c0 + c]; }
-      if (n > 0) launch_apply(h, nc, mp, T, n, C, c0, apply_smem, s);
+      if (n > 0) launch_apply(h, nc, mp, T, n, Cp, c0, apply_smem, s);
     }
   }
   *iterations_out = iterations;

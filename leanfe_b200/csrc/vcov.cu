@@ -276,8 +276,14 @@ template <int NC>
 __global__ void __launch_bounds__(PJ_T) k_resid_scores(const double* __restrict__ y, ColPtrs X,
                                                        const double* __restrict__ beta_full,
                                                        const double* __restrict__ w, const int32_t* __restrict__ key,
-                                                       int64_t n, double* __restrict__ S, uint32_t* __restrict__ present,
-                                                       double* __restrict__ partials, int use_shift, bool vec_codes) {
+                                                       int64_t n, double* __restrict__ S, int ldS,
+                                                       uint32_t* __restrict__ present, double* __restrict__ partials,
+                                                       int use_shift, bool vec_codes, bool bulk) {
+  // bulk: score rows leave as one TMA reduce each (segreduce.cuh: bulk_add_row) unless neighbouring rows share a
+  // cluster; the per-thread staging slots are the dynamic shared memory
+  extern __shared__ __align__(16) double rs_slots[];
+  double* my_slots = rs_slots + (size_t)threadIdx.x * BulkRow<NC>::SLOT_DOUBLES;
+  int slot = 0;
   __shared__ double sb[NC + 1];
   if (threadIdx.x <= NC) sb[threadIdx.x] = beta_full[threadIdx.x];
   __syncthreads();
@@ -312,8 +318,15 @@ __global__ void __launch_bounds__(PJ_T) k_resid_scores(const double* __restrict_
       for (int c = 0; c < NC; ++c) v[e][c] *= rw;
       if (valid) present[kk[e]] = 1u;
     }
-    segmented_flush<NC>(kk, v, S, NC, 0, 1);
+    if (bulk && warp_keys_all_distinct_neighbours(kk)) {
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e)
+        if (kk[e] >= 0) bulk_add_row<NC>(S + (size_t)kk[e] * ldS, v[e], my_slots, slot);
+    } else {
+      segmented_flush<NC>(kk, v, S, ldS, 0, 1);
+    }
   }
+  if (bulk) bulk_add_drain();
   __shared__ double sh[PJ_T / 32][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
@@ -334,15 +347,19 @@ static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, i
   for (int j = 0; j < k; ++j) X.col[j] = cols[1 + j];
   const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   const int blocks = launch_blocks(h, nchunk, 8);
-  DevBuf<double> S((size_t)Gcap * k, s), partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
+  const int ldS = (k + 1) & ~1;   // score rows padded to a 16-byte multiple (TMA bulk reduce); the pad stays zero
+  DevBuf<double> S((size_t)Gcap * ldS, s), partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
   DevBuf<uint32_t> present(Gcap, s);
   DevBuf<unsigned long long> tot(1, s);
   S.zero(); present.zero(); tot.zero();
   const bool vec = (((uintptr_t)cl) & 15) == 0;
   const int shift = h->world == 1 ? 1 : 0;
+  const bool bulk = n >= 4096;
+  const size_t slot_bytes = bulk ? (size_t)PJ_T * BR_SLOTS * ldS * sizeof(double) : 0;
 #define RS_CASE(NC_)                                                                                              \
   case NC_:                                                                                                       \
-    k_resid_scores<NC_><<<blocks, PJ_T, 0, s>>>(cols[0], X, beta_full, weights, cl, n, S, present, partials, shift, vec); \
+    k_resid_scores<NC_><<<blocks, PJ_T, slot_bytes, s>>>(cols[0], X, beta_full, weights, cl, n, S, ldS, present,  \
+                                                         partials, shift, vec, bulk);                             \
     break;
   switch (k) { RS_CASE(1) RS_CASE(2) RS_CASE(3) RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8) }
 #undef RS_CASE
@@ -363,10 +380,10 @@ static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, i
   // meat = S'S (cross-rank: sum the score table for shared clusters, the k x k meats for rank-local ones)
   DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
   V.zero();
-  if (h->world > 1 && !cl_local) comm_allreduce(h, S, Gcap * k, 0, s);
+  if (h->world > 1 && !cl_local) comm_allreduce(h, S, Gcap * ldS, 0, s);
   std::vector<const double*> sc(k);
   for (int c = 0; c < k; ++c) sc[c] = S.p + c;
-  gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, k);
+  gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, ldS);
   if (h->world > 1 && cl_local) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
   k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
   KERNEL_CHECK();
