@@ -358,6 +358,9 @@ static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, i
   const size_t slot_bytes = bulk ? (size_t)PJ_T * BR_SLOTS * ldS * sizeof(double) : 0;
 #define RS_CASE(NC_)                                                                                              \
   case NC_:                                                                                                       \
+    if (slot_bytes > 40 * 1024)                                                                                   \
+      CUDA_CHECK(cudaFuncSetAttribute(k_resid_scores<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                      (int)slot_bytes));                                                          \
     k_resid_scores<NC_><<<blocks, PJ_T, slot_bytes, s>>>(cols[0], X, beta_full, weights, cl, n, S, ldS, present,  \
                                                          partials, shift, vec, bulk);                             \
     break;
