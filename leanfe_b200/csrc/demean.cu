@@ -846,7 +846,8 @@ static void launch_s0_fused(lfe_ctx* h, int nc, const int32_t* const* codes, con
     }
   }
   // TMA bulk reduce for the rows of the big tables: needs 16-byte aligned table rows (even ld / column offset)
-  bool bulk = (ld_acc % 2 == 0) && (acc_col0 % 2 == 0);
+  // (for one or two columns the plain REDs are as fast as the bulk request)
+  bool bulk = nc >= 3 && (ld_acc % 2 == 0) && (acc_col0 % 2 == 0);
   bool any_red = false;
   for (int j = 0; j < F; ++j)
     if (sp.smem_off[j] < 0) { any_red = true; bulk = bulk && aligned16(acc[j]); }
@@ -1058,9 +1059,11 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
   const int32_t* const* codes = plan->codes;
   std::vector<FEState>& st = plan->st;
   LFE_REQUIRE(C >= 1, "lfe_demean: C must be >= 1");
-  // leading dimension of every FE table: C rounded up to even, so table rows are 16-byte aligned (128-bit
-  // gathers, TMA bulk reduces); the pad column stays zero throughout
-  const int Cp = (C + 1) & ~1;
+  // leading dimension of every FE table: an odd C >= 5 is rounded up to even, so table rows are 16-byte aligned
+  // (128-bit gathers, TMA bulk reduces); the pad column stays zero throughout.  Narrow tables are left alone:
+  // padding 3 -> 4 columns makes c3's 240 MB worker table 320 MB and its random gathers 20 % slower (L2 hit
+  // rate), and 1 -> 2 would double every table of the per-column runs.
+  const int Cp = (C >= 5 && (C & 1)) ? C + 1 : C;
   LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
   {
     bool seen[LFE_MAX_FE] = {false};

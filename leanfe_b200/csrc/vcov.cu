@@ -347,15 +347,17 @@ static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, i
   for (int j = 0; j < k; ++j) X.col[j] = cols[1 + j];
   const int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   const int blocks = launch_blocks(h, nchunk, 8);
-  const int ldS = (k + 1) & ~1;   // score rows padded to a 16-byte multiple (TMA bulk reduce); the pad stays zero
+  // score rows padded to a 16-byte multiple for the TMA bulk reduce (k = 5 -> 6; the pad stays zero); narrow
+  // rows keep their width and the RED path
+  const int ldS = (k >= 5 && (k & 1)) ? k + 1 : k;
   DevBuf<double> S((size_t)Gcap * ldS, s), partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
   DevBuf<uint32_t> present(Gcap, s);
   DevBuf<unsigned long long> tot(1, s);
   S.zero(); present.zero(); tot.zero();
   const bool vec = (((uintptr_t)cl) & 15) == 0;
   const int shift = h->world == 1 ? 1 : 0;
-  const bool bulk = n >= 4096;
-  const size_t slot_bytes = bulk ? (size_t)PJ_T * BR_SLOTS * ldS * sizeof(double) : 0;
+  const bool bulk = n >= 4096 && k >= 3 && (ldS & 1) == 0;
+  const size_t slot_bytes = bulk ? (size_t)PJ_T * BR_SLOTS * ((k + 1) & ~1) * sizeof(double) : 0;
 #define RS_CASE(NC_)                                                                                              \
   case NC_:                                                                                                       \
     if (slot_bytes > 40 * 1024)                                                                                   \
