@@ -121,6 +121,32 @@ class ClockSampler:
                 "samples": len(inside), "reasons": reasons}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned buffers) to the NUMA
+    node its GPU hangs off, so the H2D copies of the end-to-end arm do not cross the socket interconnect when
+    eight ranks share one host.  Best effort: returns a short description, never raises."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            return {"node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:       # no sysfs / no permission / old torch: run unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
 def cpu_reference_run(d: dict, steps: int, warmup: int):
     """Time the reference algorithm (OpenMP C port of polars_impl.py:468-537 + std_errors.py:289-347)."""
     from oracle import ref_port as P
@@ -177,6 +203,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = get_engine(local_rank)
@@ -313,7 +340,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "rows_total": total_rows, "sweeps": sweeps, "converged": bool(res.converged),
                    "l2": "inputs (3.2 GB/GPU) exceed the 126 MB L2; no explicit flush", "tol": 1e-6,
-                   "parallelism": f"row-sharded by unit x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"row-sharded by unit x{world}" if world > 1 else "single GPU",
+                   "host_numa": numa},
         "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * (2 * K_REG + 3),
                 "ms_per_step": e2e_ms / args.steps,
                 # the same 3.2 GB copied host -> device with nothing else running: what PCIe alone costs per step
