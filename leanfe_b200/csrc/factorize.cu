@@ -287,11 +287,16 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
     h->n_launches += 2;
     if (want_counts && G > 0) {
       h->last_counts.alloc(G, s);
-      k_compact_counts<<<launch_blocks(h, ceil_div64(range, 256 * 4), 8), 256, 0, s>>>(cnt, rank, range, h->last_counts);
-      KERNEL_CHECK();
-      h->last_counts_G = G;
-      h->last_counts_codes = codes;
-      h->n_launches += 1;
+      if (h->last_counts.p) {   // (allocation failure just means "no counts": the caller falls back to lfe_group_counts)
+        k_compact_counts<<<launch_blocks(h, ceil_div64(range, 256 * 4), 8), 256, 0, s>>>(cnt, rank, range,
+                                                                                        h->last_counts);
+        KERNEL_CHECK();
+        h->last_counts_G = G;
+        h->last_counts_codes = codes;
+        h->n_launches += 1;
+      } else {
+        (void)cudaGetLastError();   // clear the allocation error
+      }
     }
     if (uniques && G <= uniques_cap) {
       int b2 = launch_blocks(h, ceil_div64(range, 256 * 4), 8);
