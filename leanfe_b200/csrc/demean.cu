@@ -588,37 +588,47 @@ __global__ void __launch_bounds__(256, 2) k_apply4(MutColPtrs cols, ApplyTabs T,
   const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
   const int64_t n4 = n >> 2;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
-    double s[4][NC];
+    // all column loads first: they depend on nothing, and (dst may alias src) none of them may be ordered after
+    // a store of this iteration; the gathered table rows are then subtracted in place
+    double2 xa[NC], xb[NC];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) s[e][c] = 0.0;
+    for (int c = 0; c < NC; ++c) {
+      xa[c] = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g);
+      xb[c] = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g + 1);
+    }
     for (int j = 0; j < T.n; ++j) {
       const int4 k4 = __ldcs(reinterpret_cast<const int4*>(T.code[j]) + g);
-      const int k[4] = {k4.x, k4.y, k4.z, k4.w};
       const double* tab = tabs[j] + col0;
+      const double* r0 = tab + (size_t)k4.x * ldc;
+      const double* r1 = tab + (size_t)k4.y * ldc;
+      const double* r2 = tab + (size_t)k4.z * ldc;
+      const double* r3 = tab + (size_t)k4.w * ldc;
+      if (vec2) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double* row = tab + (size_t)k[e] * ldc;
-        if (vec2) {
+        for (int c = 0; c < NC / 2; ++c) {
+          const double2 t0 = *(reinterpret_cast<const double2*>(r0) + c);
+          const double2 t1 = *(reinterpret_cast<const double2*>(r1) + c);
+          const double2 t2 = *(reinterpret_cast<const double2*>(r2) + c);
+          const double2 t3 = *(reinterpret_cast<const double2*>(r3) + c);
+          xa[2 * c].x -= t0.x; xa[2 * c + 1].x -= t0.y;
+          xa[2 * c].y -= t1.x; xa[2 * c + 1].y -= t1.y;
+          xb[2 * c].x -= t2.x; xb[2 * c + 1].x -= t2.y;
+          xb[2 * c].y -= t3.x; xb[2 * c + 1].y -= t3.y;
+        }
+      } else {
 #pragma unroll
-          for (int c = 0; c < NC / 2; ++c) {
-            const double2 t = *(reinterpret_cast<const double2*>(row) + c);
-            s[e][2 * c] += t.x;
-            s[e][2 * c + 1] += t.y;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) s[e][c] += row[c];
+        for (int c = 0; c < NC; ++c) {
+          xa[c].x -= r0[c];
+          xa[c].y -= r1[c];
+          xb[c].x -= r2[c];
+          xb[c].y -= r3[c];
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const double2 a = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g);
-      const double2 b = __ldcs(reinterpret_cast<const double2*>(cols.src[c]) + 2 * g + 1);
-      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g, make_double2(a.x - s[0][c], a.y - s[1][c]));
-      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g + 1, make_double2(b.x - s[2][c], b.y - s[3][c]));
+      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g, xa[c]);
+      __stcs(reinterpret_cast<double2*>(cols.col[c]) + 2 * g + 1, xb[c]);
     }
   }
   // the last n % 4 rows
