@@ -174,3 +174,57 @@ def test_oracle_against_live_reference_functions():
         np.testing.assert_allclose(list(r["std_errors"].values()), rr["se"], rtol=1e-9)
     for f in ("y ~ x1 + i(region, ref=B) + t:i(g) | a + b", "y ~ x | fe | z1 + z2"):
         assert tuple(ref.common.parse_formula(f)) == tuple(O.parse_formula(f))
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_window_semantics_against_a_dataframe_engine(weighted):
+    """The one part of the path no reference code can pin here (Polars is not installable) is the window
+    arithmetic `col - col.mean().over(fe)` / `len().over(fe) > 1` (polars_impl.py:478-508).  pandas'
+    groupby-transform is the same window semantics in an independent engine: the oracle's singleton filter,
+    Gauss-Seidel sweeps (FE order, weighted means) and y-only unweighted stopping test must agree with the
+    reference loop written literally against pandas."""
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(7)
+    n = 6000
+    df = pd.DataFrame({"unit": rng.integers(0, 900, n), "firm": rng.integers(0, 60, n), "year": rng.integers(0, 7, n)})
+    df["unit"] = np.where(rng.random(n) < 0.02, 10_000 + np.arange(n), df["unit"])      # some singleton units
+    for c in ("y", "x1", "x2"):
+        df[c] = rng.normal(size=n) + 0.3 * (df["unit"] % 13) + 0.2 * df["firm"] + 0.1 * df["year"]
+    df["w"] = rng.uniform(0.5, 2.0, n)
+    fes, cols = ["unit", "firm", "year"], ["y", "x1", "x2"]
+
+    # --- the reference loop, literally (polars_impl.py:478-526), on pandas -------------------------
+    card = {f: df[f].nunique() for f in fes}                                  # :371-373, pre-drop
+    keep = np.ones(n, dtype=bool)
+    for f in fes:                                                             # :478-482, evaluated once
+        keep &= (df.groupby(f)[f].transform("size") > 1).to_numpy()
+    d = df[keep].reset_index(drop=True)
+    order = sorted(fes, key=lambda f: card[f])                                # :485
+    tol, max_iter, iters = 1e-8, 50, 0
+    for it in range(1, max_iter + 1):
+        for f in order:                                                       # :490-508
+            for c in cols:
+                if weighted:
+                    num = (d[c] * d["w"]).groupby(d[f]).transform("sum")
+                    den = d["w"].groupby(d[f]).transform("sum")
+                    d[c] = d[c] - num / den
+                else:
+                    d[c] = d[c] - d.groupby(f)[c].transform("mean")
+        iters = it
+        if it >= 3:                                                           # :511-525, y only, unweighted
+            mm = max(float(d.groupby(f)["y"].transform("mean").abs().max()) for f in fes)
+            if mm < tol:
+                break
+
+    # --- the oracle ---------------------------------------------------------------------------------
+    codes = [O.codes_sorted(df[f].to_numpy())[0] for f in fes]
+    k_or = O.singleton_keep_mask(codes)
+    np.testing.assert_array_equal(k_or, keep)
+    kc = [c[k_or] for c in codes]
+    o_order = O.fe_order([card[f] for f in fes])
+    assert [fes[j] for j in o_order] == order
+    o_cols, o_it, o_mm = O.alt_proj([df[c].to_numpy()[k_or] for c in cols], kc, o_order, tol, max_iter,
+                                    df["w"].to_numpy()[k_or] if weighted else None)
+    assert o_it == iters
+    for c, got in zip(cols, o_cols):
+        np.testing.assert_allclose(got, d[c].to_numpy(), rtol=0, atol=1e-11)
