@@ -323,7 +323,9 @@ def main():
         # ncu dram__bytes_read+write of the two projection launches of one sweep at this exact config
         # (profiles/r1_ncu_top_kernels_s2.md: k_proj_q 0.260 GB + k_proj 0.266 GB); null at other sizes
         "traffic": 0.526e9 if (n == 50_000_000 and world == 1) else None,
-        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (84 % / 61 % of peak, "
+        "basis": "achieved/frac = bytes this implementation's sweep must move (packed code words + tables) / time; "
+                 "inplace_equivalent = SURVEY 8(d) bytes of the reference's in-place sweep / the same time",
+        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (84 % / 78 % of peak, "
                    "profiles/r1_ncu_top_kernels_s2.md); the sweep reads only the packed code words",
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
         "proj_launches_per_fit": proj_launches,
