@@ -5,15 +5,26 @@ clustered by unit) and the demean-sweep roofline, with the reference algorithm t
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
 
 A "step" is one complete fit through the public API (`leanfe_b200.leanfe`): factorise the raw int64
-ids, singleton filter, order rows by unit, alternating projections to the reference's tolerance, Gram,
+ids, singleton filter, entry lists, alternating projections to the reference's tolerance, Gram,
 Cholesky solve, cluster-robust sandwich.  `value` = rows/s with the inputs already resident in HBM;
-`e2e` = the same call on pinned HOST tensors (H2D inside the timed region, result read back).
+`e2e` = the same call on pinned HOST tensors (H2D inside the timed region, result read back);
+`e2e_pageable` / `e2e_pandas` = the same call on a plain NumPy dict / a pandas DataFrame (what the
+reference API receives, polars_impl.py:342-347).
 With N > 1 (torchrun) every rank owns a disjoint block of units (weak scaling: 50M rows per GPU); the
-time-FE tables, Gram and meat are all-reduced over NCCL inside liblfe.
+time-FE tables, Gram and meat are all-reduced over NCCL inside liblfe.  Before the timed region a multi-GPU
+run checks the sharded fits against the single-process oracle (`mg_parity`), and every run adds a
+`c5_strong` record: BASELINE config 5 (400M rows, 10 regressors, two-way FE) generated on the device by a
+counter-based RNG keyed by the GLOBAL row index -- the same panel at every N -- split into arbitrary
+(contiguous-index) row shards that the library repartitions by unit itself.
+
+The CPU arm (`cpu_baseline`, `--impl reference`) fits the SAME full panel on all host cores: the real
+reference through Polars when `import polars` works on the box, else the OpenMP C port of its algorithm
+(oracle/ref_port.c).  `parity` compares the 50M-row GPU fit with that CPU fit.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -30,9 +41,12 @@ K_REG = 5
 N_TIME = 500
 ROWS_PER_UNIT = 50
 FORMULA = "y ~ x1 + x2 + x3 + x4 + x5 | unit + time"
+C5_K = 10
+C5_ROWS_PER_UNIT = 100
+C5_FORMULA = "y ~ " + " + ".join(f"x{j}" for j in range(1, C5_K + 1)) + " | unit + time"
 
 
-def make_panel(n_rows: int, seed: int, unit_offset: int = 0, out=None):
+def make_panel(n_rows: int, seed: int, unit_offset: int = 0):
     """unit ~ U{0..N/50}, time ~ U{0..500}, x_j ~ N(0,1) + 0.5 a_unit,
     eps = s_unit * N(0,1) with s ~ U(0.5, 1.5), y = sum (1 + 0.1 j) x_j + a_unit + g_time + eps."""
     rng = np.random.default_rng(seed)
@@ -63,6 +77,61 @@ def sample_for_cpu(d: dict, G1: int, target_rows: int):
     base = int(d["unit"].min())
     m = (d["unit"] - base) < cut
     return {k: v[m] for k, v in d.items()}, int(m.sum())
+
+
+# ---- c5: counter-based device generator (same panel for every world size) ---------------------------
+_M64 = (1 << 64) - 1
+
+
+def _i64(c: int) -> int:
+    c &= _M64
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _mix(torch, z):
+    """splitmix64 finaliser on an int64 tensor (two's-complement wrap-around arithmetic, logical shifts)."""
+    z = z + _i64(0x9E3779B97F4A7C15)
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _i64(0x94D049BB133111EB)
+    return z ^ ((z >> 31) & ((1 << 33) - 1))
+
+
+def _uniform(torch, idx, stream: int):
+    """U(0,1) keyed by (stream, idx): 53 random bits."""
+    h = _mix(torch, idx * _i64(0xD1342543DE82EF95) + _i64(stream * 0x632BE59BD9B4E019 + 0x1234567))
+    return (((h >> 11) & ((1 << 53) - 1)).to(torch.float64) + 0.5) * (1.0 / (1 << 53))
+
+
+def _normal(torch, idx, stream: int):
+    u1, u2 = _uniform(torch, idx, 2 * stream), _uniform(torch, idx, 2 * stream + 1)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos((2.0 * np.pi) * u2)
+
+
+def make_c5_rows(torch, dev, lo: int, hi: int, n_total: int, chunk: int = 25_000_000):
+    """Rows [lo, hi) of the c5 panel: unit ~ U{0..N/100}, time ~ U{0..500}, 10 regressors
+    x_j ~ N(0,1) + 0.5 a_unit, y = sum (1 + 0.05 j) x_j + a_unit + g_time + N(0,1).  Every value is a pure function
+    of the GLOBAL row index (and of the unit / period id for a, g), so 1/2/4/8-GPU runs see identical data."""
+    G1 = max(n_total // C5_ROWS_PER_UNIT, 2)
+    n = hi - lo
+    out = {nm: torch.empty(n, dtype=torch.float64, device=dev) for nm in ["y"] + [f"x{j}" for j in range(1, C5_K + 1)]}
+    out["unit"] = torch.empty(n, dtype=torch.int64, device=dev)
+    out["time"] = torch.empty(n, dtype=torch.int64, device=dev)
+    for a in range(lo, hi, chunk):
+        b = min(a + chunk, hi)
+        sl = slice(a - lo, b - lo)
+        idx = torch.arange(a, b, dtype=torch.int64, device=dev)
+        unit = (_uniform(torch, idx, 1) * G1).to(torch.int64).clamp_(max=G1 - 1)
+        tm = (_uniform(torch, idx, 2) * N_TIME).to(torch.int64).clamp_(max=N_TIME - 1)
+        au = _normal(torch, unit, 50)
+        y = au + _normal(torch, tm, 51) + _normal(torch, idx, 52)
+        for j in range(1, C5_K + 1):
+            x = _normal(torch, idx, 100 + j) + 0.5 * au
+            y += (1 + 0.05 * j) * x
+            out[f"x{j}"][sl] = x
+        out["y"][sl] = y
+        out["unit"][sl] = unit
+        out["time"][sl] = tm
+    return out
 
 
 class ClockSampler:
@@ -147,18 +216,74 @@ def bind_to_gpu_numa_node(local_rank: int):
         return {"bound": False, "why": type(e).__name__}
 
 
+# ---- the CPU arm: the real reference when Polars is importable, else the OpenMP port ------------------
+def live_reference():
+    """Probe for the UNMODIFIED reference (python/leanfe/leanfe.py:14-184 -> polars_impl.py:468-537).  It needs
+    Polars, which this image does not ship; `baseline/_ref` holds the reference package itself (pip --no-deps).
+    -> (callable | None, why)"""
+    try:
+        import polars  # noqa: F401
+    except Exception as e:
+        return None, f"import polars failed ({type(e).__name__}): the reference's engine is not installed on this box"
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/python"):
+        if os.path.isdir(os.path.join(cand, "leanfe")) and cand not in sys.path:
+            sys.path.insert(0, cand)
+    try:
+        from leanfe import leanfe as ref_leanfe
+        return ref_leanfe, "polars importable"
+    except Exception as e:
+        return None, f"polars importable but `import leanfe` failed ({type(e).__name__}: {e})"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(d: dict, steps: int, warmup: int):
-    """Time the reference algorithm (OpenMP C port of polars_impl.py:468-537 + std_errors.py:289-347)."""
-    from oracle import ref_port as P
+    """Time the reference's algorithm on ALL host cores on the panel `d`.  -> dict(rate, cores, kind, note, sec,
+    beta, se, iterations, n_obs)"""
     X = [d[f"x{j}"] for j in range(1, K_REG + 1)]
     n = d["y"].shape[0]
-    times, res = [], None
+    ref_leanfe, why = live_reference()
+    times = []
+    if ref_leanfe is not None:
+        import polars as pl
+        df = pl.DataFrame({k: v for k, v in d.items()})
+        res = None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = ref_leanfe(df, formula=FORMULA, vcov="cluster", cluster_cols=["unit"], backend="polars", strategy="alt_proj")
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        names = [f"x{j}" for j in range(1, K_REG + 1)]
+        return dict(rate=n * len(times) / sum(times), cores=host_cores(), kind="reference", note=why,
+                    sec=float(np.mean(times)), beta=np.array([res["coefficients"][c] for c in names]),
+                    se=np.array([res["std_errors"][c] for c in names]), iterations=int(res["iterations"]),
+                    n_obs=int(res["n_obs"]))
+    from oracle import ref_port as P
+    cores = P.set_threads(host_cores())      # torchrun exports OMP_NUM_THREADS=1 to its workers: set it explicitly
+    res = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         res = P.fit(d["y"], X, [d["unit"], d["time"]], cluster=d["unit"], vcov="cluster", ssc=True, tol=1e-6, max_iter=50)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return n * len(times) / sum(times), P.threads(), res, float(np.mean(times))
+    return dict(rate=n * len(times) / sum(times), cores=cores, kind="port",
+                note=f"OpenMP C restatement of the reference algorithm (oracle/ref_port.c); live reference unavailable: {why}",
+                sec=float(np.mean(times)), beta=res["beta"], se=res["se"], iterations=res["iterations"], n_obs=res["n_obs"])
+
+
+def ncu_traffic(key: str):
+    """dram__bytes_read + dram__bytes_write of one sweep's projection launches, from the committed ncu summary."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(key)
+        return (float(e["bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 def main():
@@ -168,31 +293,39 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=50_000_000, help="rows per GPU")
-    ap.add_argument("--cpu-rows", type=int, default=10_000_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU arm (default: the full per-GPU panel)")
+    ap.add_argument("--c5-rows", type=int, default=400_000_000, help="TOTAL rows of the c5 strong-scaling record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arms (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the c5 strong-scaling record")
+    ap.add_argument("--no-mg-parity", action="store_true", help="skip the multi-GPU oracle check (world > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu_rows = args.rows if args.cpu_rows is None else args.cpu_rows
     workload = f"c2: {args.rows // 1_000_000}M rows/GPU, 5 regressors | unit({args.rows // ROWS_PER_UNIT}) + time(500), cluster(unit), ssc"
 
     if args.impl == "reference":
         if rank != 0:
             return
         d, G1 = make_panel(args.rows, 42)
-        ds, ns = sample_for_cpu(d, G1, args.cpu_rows)
+        ds, ns = sample_for_cpu(d, G1, cpu_rows)
         del d
-        rate, cores, res, sec = cpu_reference_run(ds, args.steps, max(args.warmup, 1))
-        sample = f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the {args.rows}-row panel"
+        r = cpu_reference_run(ds, args.steps, max(args.warmup, 1))
+        sample = (f"the full {ns}-row panel of one GPU" if ns == args.rows else
+                  f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the {args.rows}-row panel")
+        if args.gpus > 1:
+            sample += f" (the {args.gpus}-GPU arm fits {args.gpus} such shards, weak scaling)"
         print(json.dumps({
-            "impl": "reference", "metric": "fit rows/s", "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "impl": "reference", "metric": "fit rows/s", "value": r["rate"], "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": r["sec"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample, "sweeps": res["iterations"]},
-            "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample,
-                             "note": "OpenMP C restatement of the reference algorithm (Polars 1.36.1 not installable)"},
-            "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": workload, "sample": sample, "sweeps": r["iterations"]},
+            "cpu_baseline": {"value": r["rate"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                             "note": r["note"], "host_cpus": os.cpu_count()},
+            "e2e": {"value": r["rate"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "coefs": {f"x{j + 1}": float(b) for j, b in enumerate(r["beta"])},
         }))
         return
 
@@ -210,6 +343,29 @@ def main():
     if world > 1:
         eng.comm_init_from_torch()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- multi-GPU parity against the single-process oracle, before anything is timed ------------------
+    mg_parity = None
+    if world > 1 and not args.no_mg_parity:
+        spec = importlib.util.spec_from_file_location("multigpu_check", os.path.join(ROOT, "tests", "multigpu_check.py"))
+        mgc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mgc)
+        t0 = time.perf_counter()
+        fails = mgc.run_checks(rank, world)
+        bad = torch.tensor([float(len(fails))], dtype=torch.float64, device=dev)
+        dist.all_reduce(bad)
+        mg_parity = {"ok": int(bad.item()) == 0, "world": world, "failed_cases_over_ranks": int(bad.item()),
+                     "cases": "two-way iid/hc1/cluster(unit)/cluster(time) pre-partitioned + arbitrary shards "
+                              "(library repartition); three-way weighted / hc1 / cluster(firm) both ways; YOCO x5",
+                     "tolerance": "beta 1e-8, se 1e-6, iterations / n_obs / df_resid / fe_dims / n_clusters equal, "
+                                  "results bit-identical on all ranks", "seconds": round(time.perf_counter() - t0, 1)}
+        if fails and rank == 0:
+            print(f"mg_parity FAILED: {fails[:2]}", file=sys.stderr)
+
     # ---- synthetic panel in pinned host memory (rank r owns units [r*G1, (r+1)*G1)) ---------------
     n = args.rows
     d, G1 = make_panel(n, 42 + rank, unit_offset=rank * max(n // ROWS_PER_UNIT, 2))
@@ -222,11 +378,6 @@ def main():
     kw = dict(formula=FORMULA, vcov="cluster", cluster_cols=["unit"], strategy="alt_proj")
     if world > 1:
         kw["local_fe"] = "unit"      # rows are sharded by unit: its tables, counts and cluster scores stay rank-local
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
 
     # ---- device-resident arm ----------------------------------------------------------------------
     resident = {k_: t.to(dev) for k_, t in host.items()}
@@ -253,9 +404,21 @@ def main():
     del resident
     torch.cuda.empty_cache()
 
-    # ---- end-to-end arm: pinned host buffers -> public API -> result on the host ------------------
+    # ---- end-to-end arms: host buffers -> public API -> result on the host ------------------------
+    def timed_e2e(data, steps):
+        for _ in range(max(1, min(args.warmup, 2))):
+            leanfe(data, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r2 = leanfe(data, **kw)
+            _ = float(r2.coefs["x1"])
+        barrier()
+        return (time.perf_counter() - t0) / steps
+
     e2e_s = float("nan")
     h2d_only_ms = None
+    e2e_extra = {}
     if not args.no_e2e:
         # the PCIe floor of the end-to-end arm: the same host tensors copied to the device with no compute
         dst = {k_: torch.empty_like(t, device=dev) for k_, t in host.items()}
@@ -269,15 +432,22 @@ def main():
         barrier()
         h2d_only_ms = c0.elapsed_time(c1) / 3
         del dst
-        for _ in range(max(1, min(args.warmup, 2))):
-            leanfe(host, **kw)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r2 = leanfe(host, **kw)
-            _ = float(r2.coefs["x1"])
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        e2e_s = timed_e2e(host, args.steps) * args.steps
+        if world == 1:
+            # what the reference API actually receives: pageable NumPy columns / a pandas frame
+            sec = timed_e2e(d, max(2, args.steps // 2))
+            e2e_extra["e2e_pageable"] = {"value": n / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
+                                         "input": "dict of pageable NumPy arrays (int64 ids, float64 columns)",
+                                         "h2d_bytes_per_step": h2d_bytes}
+            try:
+                import pandas as pd
+                pdf = pd.DataFrame(d, copy=False)
+                sec = timed_e2e(pdf, max(2, args.steps // 2))
+                e2e_extra["e2e_pandas"] = {"value": n / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
+                                           "input": "pandas DataFrame", "h2d_bytes_per_step": h2d_bytes}
+                del pdf
+            except Exception as e:       # pandas missing: report, do not fail the bench
+                e2e_extra["e2e_pandas"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if world > 1:
         tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -285,6 +455,48 @@ def main():
         ms, e2e_ms = float(tt[0]), float(tt[1])
     else:
         e2e_ms = e2e_s * 1e3
+    del host
+    if world > 1:
+        del d
+
+    # ---- c5 strong scaling: the SAME 400M-row panel at every N, arbitrary row shards in -----------------
+    c5 = None
+    if not args.no_c5:
+        torch.cuda.empty_cache()
+        n5 = args.c5_rows
+        lo5, hi5 = n5 * rank // world, n5 * (rank + 1) // world
+        shard5 = make_c5_rows(torch, dev, lo5, hi5, n5)
+        kw5 = dict(formula=C5_FORMULA, vcov="cluster", cluster_cols=["unit"], strategy="alt_proj")
+        r5 = leanfe(shard5, **kw5)       # warm-up (NCCL all-to-all buffers, pool growth)
+        eng.set_profiling(True)
+        eng.reset_timers()
+        barrier()
+        steps5 = 2
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(steps5):
+            r5 = leanfe(shard5, **kw5)
+        a1.record()
+        barrier()
+        ms5 = a0.elapsed_time(a1) / steps5
+        t5 = eng.timers()
+        eng.set_profiling(False)
+        if world > 1:
+            tt = torch.tensor([ms5], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms5 = float(tt[0])
+        c5 = {"workload": f"c5: {n5 // 1_000_000}M rows TOTAL, 10 regressors | unit({n5 // C5_ROWS_PER_UNIT}) + time(500), "
+                          "cluster(unit); identical panel at every N (counter-based RNG keyed by global row index)",
+              "scaling": "strong", "n_gpus": world, "rows_total": n5, "ms_per_fit": ms5, "value": n5 / (ms5 / 1e3),
+              "unit": "rows/s", "input": "device-resident, rows sharded by contiguous global row index (arbitrary w.r.t. unit); "
+              "the library repartitions by unit (lfe_shard_plan / lfe_shard_exchange) inside the timed region",
+              "sweeps": r5.iterations, "n_obs": r5.n_obs,
+              "phases_ms_per_fit": {k_: round(v / steps5, 3) for k_, v in t5.items() if v > 0},
+              "coefs": {k_: float(v) for k_, v in r5.coefs.items()},
+              "std_errors": {k_: float(v) for k_, v in r5.std_errors.items()}}
+        del shard5
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -303,7 +515,6 @@ def main():
 
     # ---- roofline of the demean sweep (dominant iterative kernel k_proj) -----------------------------
     C, F = K_REG + 1, 2
-    counters = {k_: v for k_, v in counters.items()}
     sweeps = res.iterations
     # every k_proj launch (regular sweeps + the speculative first projection of the stopping test, which is the
     # next sweep's first step) is timed by the library's CUDA events on the launching stream
@@ -316,17 +527,16 @@ def main():
     G_unit, G_time = n // ROWS_PER_UNIT, N_TIME
     own_bytes = F * n * 4 + 5 * 8 * C * (G_unit + G_time)
     inplace_bytes = n * F * (16 * C + 8)                    # the reference's in-place formulation
+    traffic, traffic_src = ncu_traffic("c2_50M_sweep") if (n == 50_000_000 and world == 1) else (None, None)
     roofline = {
         "bound": "hbm", "kernel": "k_proj_q<6> (time FE) + k_proj<6> (unit FE) + k_finalize (one sweep = 2 projections)",
         "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak,
-        # ncu dram__bytes_read+write of the two projection launches of one sweep at this exact config
-        # (profiles/r1_ncu_top_kernels_s2.md: k_proj_q 0.260 GB + k_proj 0.266 GB); null at other sizes
-        "traffic": 0.526e9 if (n == 50_000_000 and world == 1) else None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "basis": "achieved/frac = bytes this implementation's sweep must move (packed code words + tables) / time; "
                  "inplace_equivalent = SURVEY 8(d) bytes of the reference's in-place sweep / the same time",
-        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (84 % / 78 % of peak, "
-                   "profiles/r1_ncu_top_kernels_s2.md); the sweep reads only the packed code words",
+        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (see profiles/); the sweep "
+                   "reads only the packed code words",
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
         "proj_launches_per_fit": proj_launches,
         "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
@@ -345,19 +555,40 @@ def main():
                    "parallelism": f"row-sharded by unit x{world}" if world > 1 else "single GPU",
                    "host_numa": numa},
         "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * (2 * K_REG + 3),
-                "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "input": "pinned host torch tensors",
                 # the same 3.2 GB copied host -> device with nothing else running: what PCIe alone costs per step
-                "h2d_only_ms_per_step": h2d_only_ms},
+                "h2d_only_ms_per_step": h2d_only_ms,
+                "h2d_aggregate_gbs": (h2d_bytes * world / (h2d_only_ms / 1e3) / 1e9) if h2d_only_ms else None},
         "gpu_launches": int(counters["launches"]),
+        "collectives_per_fit": counters["collectives"] / args.steps,
         "clocks": clocks, "roofline": roofline, "phases_ms_per_step": phases,
         "coefs": {k_: float(v) for k_, v in res.coefs.items()},
     }
+    out.update(e2e_extra)
+    if mg_parity is not None:
+        out["mg_parity"] = mg_parity
+    if c5 is not None:
+        out["c5_strong"] = c5
     if world == 1 and not args.no_cpu_baseline:
-        ds, ns = sample_for_cpu(d, G1, args.cpu_rows)
-        rate, cores, pres, sec = cpu_reference_run(ds, 1, 1)
-        out["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port", "seconds": sec,
-                               "sample": f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the same panel",
-                               "sweeps": pres["iterations"]}
+        ds, ns = sample_for_cpu(d, G1, cpu_rows)
+        r = cpu_reference_run(ds, 1, 1)
+        sample = (f"the full {ns}-row panel (same arrays as the GPU fit)" if ns == n else
+                  f"{ns} rows = all rows of the first {ns // ROWS_PER_UNIT} units of the same panel")
+        out["cpu_baseline"] = {"value": r["rate"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"],
+                               "seconds": r["sec"], "sample": sample, "sweeps": r["iterations"], "note": r["note"],
+                               "host_cpus": os.cpu_count()}
+        if ns == n:
+            names = [f"x{j}" for j in range(1, K_REG + 1)]
+            gb = np.array([res.coefs[c] for c in names])
+            gs = np.array([res.std_errors[c] for c in names])
+            out["parity"] = {"against": f"cpu_baseline ({r['kind']}) on the same {n} rows",
+                             "beta_relerr": float(np.max(np.abs(gb - r["beta"]) / np.abs(r["beta"]))),
+                             "se_relerr": float(np.max(np.abs(gs - r["se"]) / np.abs(r["se"]))),
+                             "iterations_equal": bool(res.iterations == r["iterations"]),
+                             "n_obs_equal": bool(res.n_obs == r["n_obs"]),
+                             "tolerance": {"beta": 1e-8, "se": 1e-6}}
+            out["parity"]["ok"] = bool(out["parity"]["beta_relerr"] < 1e-8 and out["parity"]["se_relerr"] < 1e-6
+                                       and out["parity"]["iterations_equal"] and out["parity"]["n_obs_equal"])
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

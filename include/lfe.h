@@ -69,8 +69,8 @@ int lfe_destroy(lfe_handle h);
  * cudaEventRecord per phase.  lfe_get_timers synchronises the recorded events.
  * slots: 0 factorize, 1 counts/singletons, 2 compact, 3 sort, 4 gather, 5 demean-setup (CSR + S0),
  *        6 demean sweeps, 7 convergence checks, 8 demean apply, 9 gram, 10 solve, 11 resid/vcov,
- *        12 compress, 13 collectives.  lfe_get_counters: kernel launches since reset ([0]), sweep
- *        projection launches ([1]).                                                             */
+ *        12 compress, 13 collectives, 14 repartition.  lfe_get_counters: kernel launches since reset ([0]), sweep
+ *        projection launches ([1]), NCCL calls ([2]).                                                             */
 int lfe_set_profiling(lfe_handle h, int enabled);
 int lfe_reset_timers(lfe_handle h);
 int lfe_get_timers(lfe_handle h, double* ms_out /*[host] LFE_N_TIMERS*/);
@@ -248,6 +248,25 @@ int lfe_comm_destroy(lfe_handle h);
 /* active = 0: the calls that follow run rank-locally (no collectives) although a communicator is attached --
  * used for work that is replicated on every rank, e.g. the solve on the merged YOCO table; 1 = back on. */
 int lfe_comm_set_active(lfe_handle h, int active);
+/* Row repartition: rows arrive sharded ARBITRARILY; afterwards all rows of every group of the shard key
+ * (the highest-cardinality FE) sit on one rank, which is what lfe_singleton_mask / lfe_demean_plan_create /
+ * lfe_resid_vcov expect of `local_fe`.  Replaces nothing in the reference (single process): it is what lets the
+ * filter and FE order of polars_impl.py:478-485 be evaluated on the GLOBAL frame when the frame is spread over GPUs.
+ * lfe_shard_plan: `codes` = this rank's shard-key codes from ONE shared code space (lfe_factorize with
+ * LFE_ORDER_GLOBAL), n_groups its size.  The per-rank group sizes are all-reduced and the code axis is cut into
+ * `world` contiguous ranges balanced by row count: rank r owns codes [cuts_out[r], cuts_out[r+1]).  order_out
+ * (device, n) = this rank's row indices grouped by destination rank, original order kept inside each destination;
+ * send_counts_out[r] / recv_counts_out[r] = rows this rank sends to / receives from rank r.  Synchronises.
+ * lfe_shard_exchange: moves K columns (dtypes LFE_F64 / LFE_I32 / LFE_I64 / LFE_U8; cols_in n rows, cols_out
+ * sum(recv_counts) rows, caller-allocated) with one grouped ncclSend/ncclRecv round per column.  i32_sub (nullable,
+ * [host] K): value subtracted from an LFE_I32 column on receipt (cuts[rank] re-bases the shard key's codes to the
+ * rank-local range [0, cuts[rank+1] - cuts[rank])).  Without a communicator: order = identity, exchange = copy. */
+int lfe_shard_plan(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_groups, int64_t* cuts_out /*[host] world+1*/,
+                   int64_t* send_counts_out /*[host] world*/, int64_t* recv_counts_out /*[host] world*/,
+                   int32_t* order_out, void* stream);
+int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_counts /*[host]*/,
+                       const int64_t* recv_counts /*[host]*/, const void* const* cols_in, const int* dtypes,
+                       const int64_t* i32_sub /*[host], nullable*/, int K, int64_t n, void* const* cols_out, void* stream);
 /* sum all-reduce of a device double buffer over the attached communicator (no-op if none) */
 int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream);
 

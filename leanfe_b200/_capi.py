@@ -19,7 +19,7 @@ VCOV_IID, VCOV_HC1, VCOV_CLUSTER = 0, 1, 2
 VCOV_CLUSTER_LOCAL = 0x100
 N_TIMERS = 16
 TIMER_NAMES = ["factorize", "counts_singletons", "compact", "sort", "gather", "demean_setup", "demean_sweeps",
-               "demean_check", "demean_apply", "gram", "solve", "resid_vcov", "compress", "collectives", "_14", "_15"]
+               "demean_check", "demean_apply", "gram", "solve", "resid_vcov", "compress", "collectives", "repartition", "_15"]
 ERR_CAPACITY = -3
 
 EXPORTS = [
@@ -28,7 +28,7 @@ EXPORTS = [
     "lfe_sort_rows", "lfe_gather", "lfe_demean", "lfe_demean_plan_create", "lfe_demean_plan_run",
     "lfe_demean_plan_destroy", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
-    "lfe_allreduce_f64",
+    "lfe_allreduce_f64", "lfe_shard_plan", "lfe_shard_exchange",
 ]
 
 
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     lib.lfe_comm_set_active.argtypes = [vp, i32]
     lib.lfe_compress_merge.argtypes = [vp, P(vp), P(i64), i32, vp, vp, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
     lib.lfe_allreduce_f64.argtypes = [vp, vp, i64, vp]
+    lib.lfe_shard_plan.argtypes = [vp, vp, i64, i64, P(i64), P(i64), P(i64), vp, vp]
+    lib.lfe_shard_exchange.argtypes = [vp, vp, P(i64), P(i64), P(vp), P(i32), P(i64), i32, i64, P(vp), vp]
     for name in EXPORTS:
         if name not in ("lfe_last_error",):
             getattr(lib, name).restype = i32

@@ -4,13 +4,15 @@ Signature, defaults, strategy selection and error behaviour follow the reference
 (python/leanfe/leanfe.py:14-184 -> python/leanfe/polars_impl.py:287-579).  Everything per-row runs in
 liblfe.so (``include/lfe.h``); this module only orchestrates.  Deviations (all listed in DESIGN.md):
 'hc1' and 'HC1' are both accepted, expanded factor/interaction columns are kept (reference bug), dummy
-names use the original labels, IV is not implemented, ``compression_ratio`` is only computed when
-the strategy rule actually needs it.
+names use the original labels, IV/2SLS is implemented (single-GPU, strategies ols / demean / alt_proj;
+rejected for 'compress' and multi-GPU), ``compression_ratio`` is only computed when the strategy rule
+actually needs it.
 """
 from __future__ import annotations
 
 import contextlib
 import time
+import warnings
 
 import numpy as np
 import torch
@@ -58,9 +60,13 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     """Counterpart of ``leanfe_polars`` (polars_impl.py:287-301) on the device.
 
     Multi-GPU (one process per GPU, ``Engine.comm_init_from_torch()`` called): ``data`` holds THIS rank's
-    rows, partitioned so that the groups of fixed effect ``local_fe`` never span ranks (shard by the
-    highest-cardinality FE).  All other FE tables, the Gram matrix and the meat are all-reduced over NCCL
-    inside liblfe; every rank returns the same result.
+    rows.  With ``local_fe=None`` (default) the rows may be sharded ARBITRARILY: the library factorises every
+    key column in one shared code space, cuts the code range of the highest-cardinality FE into ``world``
+    row-balanced ranges and moves the rows with one NCCL all-to-all per column (``lfe_shard_plan`` /
+    ``lfe_shard_exchange``), so the singleton filter and FE order are those of the GLOBAL frame
+    (polars_impl.py:478-485).  ``local_fe=<name>`` declares that the caller already partitioned the rows so
+    that the groups of that FE never span ranks, and skips the exchange.  All other FE tables, the Gram matrix
+    and the meat are all-reduced over NCCL inside liblfe; every rank returns the same result.
     """
     t_start = time.perf_counter()
     if formula is not None:
@@ -110,8 +116,10 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
                                       "(pass it explicitly)")
         if strategy == "compress":
             local_fe = None          # YOCO shards rows arbitrarily: every key column uses the shared code space
-        elif local_fe is None or local_fe not in fe_cols:
-            raise ValueError("multi-GPU fit: pass local_fe=<the FE column rows are sharded by>")
+        elif local_fe is not None and local_fe not in fe_cols:
+            raise ValueError(f"multi-GPU fit: local_fe={local_fe!r} is not one of the fixed effects {fe_cols}")
+        elif not fe_cols:
+            raise ValueError("multi-GPU alt_proj / demean fits need at least one fixed effect")
         if sample_frac is not None:
             raise NotImplementedError("sample_frac is not supported in multi-GPU fits")
         if instruments:
@@ -144,6 +152,38 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     fe_keys = [key(c) for c in fe_cols]
     cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
     base_x = list(x_cols)
+    extra_z = [z for z in instruments if z not in x_cols]
+    fe_card_order = [k_.n_groups for k_ in fe_keys]      # cardinalities that fix the sweep order (:485)
+    if dist and strategy != "compress":
+        if local_fe is None:
+            # library-side repartition: all key columns are coded in the shared code space; the rows
+            # move so that every group of the highest-cardinality FE lives on one rank
+            j_sh = max(range(len(fe_cols)), key=lambda j: fe_keys[j].n_groups)
+            local_fe = fe_cols[j_sh]
+            num_names = list(dict.fromkeys([y_col] + base_x + extra_z + ([weights] if weights is not None else [])
+                                           + [v for v, _, _ in interactions]))
+            key_names = list(dict.fromkeys(fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions]
+                                           + [v for v, _ in factor_vars]))
+            for nm in [f for _, f, _ in interactions] + [v for v, _ in factor_vars]:
+                key(nm, labels=True)
+            tensors = [num(nm) for nm in num_names] + [key(nm).codes for nm in key_names]
+            sp = eng.shard_plan(fe_keys[j_sh].codes, fe_keys[j_sh].n_groups)
+            lo, hi = sp["cuts"][eng.rank], sp["cuts"][eng.rank + 1]
+            moved = eng.shard_exchange(sp, tensors, [0] * len(num_names) + [lo if nm == local_fe else 0 for nm in key_names])
+            del tensors
+            for nm, t in zip(num_names, moved):
+                numeric[nm] = t
+                owned_ids.add(id(t))
+            for nm, t in zip(key_names, moved[len(num_names):]):
+                keys[nm] = KeyColumn(t, (hi - lo) if nm == local_fe else keys[nm].n_groups, keys[nm].labels, None)
+            fe_keys = [keys[c] for c in fe_cols]
+            cl_keys = [keys[c] for c in cluster_cols] if cluster_cols else []
+        else:
+            # caller-partitioned rows: the shard key was coded rank-locally; its global cardinality (for the sweep
+            # order, which must be the same on every rank) is the sum over ranks
+            j_sh = fe_cols.index(local_fe)
+            fe_card_order[j_sh] = int(eng.allreduce(torch.tensor([float(fe_keys[j_sh].n_groups)], dtype=torch.float64,
+                                                                 device=eng.device)).item())
 
     def xsrc(name, keep_int):
         # YOCO only groups by the regressors: integer-typed columns (dummies, counts) are factorised as they are,
@@ -154,7 +194,6 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         return num(name)
 
     iv_state = {"k": None, "z_idx": []}
-    extra_z = [z for z in instruments if z not in x_cols]
 
     def columns(keep_int=False):
         """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
@@ -215,8 +254,17 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         y, X, names, w = get_columns()
         cols_cache[0] = (y[idx].contiguous(), [c[idx].contiguous() for c in X], names,
                          w[idx].contiguous() if w is not None else None)
-        fe_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in fe_keys]
-        cl_keys = [KeyColumn(k_.codes[idx].contiguous(), k_.n_groups) for k_ in cl_keys]
+        # cardinalities, group sizes and the strategy rule see the SAMPLED frame, as in the reference
+        # (polars_impl.py:359-373: sample first, n_unique afterwards): re-rank the sampled codes so that levels
+        # without a sampled row do not count towards fe_dims / df_resid
+        def resample(k_):
+            c_, G_, _ = eng.factorize(k_.codes[idx].contiguous())
+            return KeyColumn(c_, G_, None, eng.factorize_counts(c_, G_))
+
+        by_id = {id(k_): resample(k_) for k_ in {id(k_): k_ for k_ in fe_keys + cl_keys}.values()}
+        fe_keys = [by_id[id(k_)] for k_ in fe_keys]
+        cl_keys = [by_id[id(k_)] for k_ in cl_keys]
+        fe_card_order = [k_.n_groups for k_ in fe_keys]
         n0 = m
 
     fe_card = {c: k_.n_groups for c, k_ in zip(fe_cols, fe_keys)}
@@ -263,7 +311,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
         w_early = num(weights) if weights is not None else None
         res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
-                       max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None)
+                       max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None, fe_card_order)
     if profile:
         torch.cuda.synchronize(eng.device)
         res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
@@ -273,7 +321,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
 # ------------------------------------------------------------------------------------------------
 def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
-             formula, est_ratio, local_fe=-1, cl_local=False, iv=None) -> LeanFEResult:
+             formula, est_ratio, local_fe=-1, cl_local=False, iv=None, fe_card=None) -> LeanFEResult:
     """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression.
 
     ``get_columns()`` -> (y, X, names, w) is called as late as possible: the singleton test and the demean plan
@@ -289,7 +337,8 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
     if strategy != "ols":
         codes = [f.codes for f in fe_keys]
         Gs = [f.n_groups for f in fe_keys]
-        order = sorted(range(F), key=lambda j: Gs[j])  # ascending PRE-drop cardinality, stable (:485)
+        card = fe_card if fe_card is not None else Gs   # multi-GPU: the shard key's cardinality over ALL ranks
+        order = sorted(range(F), key=lambda j: card[j])  # ascending PRE-drop cardinality, stable (:485)
         # singleton filter: one pass, all FEs (polars_impl.py:478-482)
         # group sizes, shared by the filter and the plan: a by-product of the factorisation when it counted
         counts = [f.counts if f.counts is not None else eng.group_counts(f.codes, f.n_groups) for f in fe_keys]
@@ -509,7 +558,13 @@ def _solve_compressed(eng: Engine, comp, xk, kc, cl_idx, x_cols, fe_keys, k, F, 
         dm_G = fe_G if F else [1]
         scale = float(torch.max(torch.abs(cols[0])).item()) + 1.0
         order = sorted(range(len(dm_G)), key=lambda j: dm_G[j])
-        eng.demean(cols, dm_codes, dm_G, order, nn, 1e-14 * scale, 20000, 1, strict_check=True)
+        sweeps, _, converged = eng.demean(cols, dm_codes, dm_G, order, nn, 1e-14 * scale, 20000, 1, strict_check=True)
+        if not converged:
+            # the reference solves the dummy-variable system directly (compress.py:700-747); an iterative solve that
+            # stops short must not pass silently
+            warnings.warn(f"strategy='compress': the weighted FWL solve on the {G} compressed rows did not reach its "
+                          f"fixed point in {sweeps} sweeps (poorly connected fixed effects); coefficients and standard "
+                          "errors may be inaccurate", RuntimeWarning, stacklevel=3)
         gram = eng.gram(cols[1:] + [cols[0]], nn, add_intercept=False)
         beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
         p = 1 + k + sum(g - 1 for g in fe_G)
@@ -527,4 +582,5 @@ def _solve_compressed(eng: Engine, comp, xk, kc, cl_idx, x_cols, fe_keys, k, F, 
         n_clusters = out["n_clusters"][0] if len(cl_idx) == 1 else tuple(out["n_clusters"])
     return LeanFEResult(coefs=dict(zip(x_cols, host[:k].tolist())), std_errors=dict(zip(x_cols, host[k:2 * k].tolist())),
                         n_compressed=G, n_obs=n_obs, vcov_type=vcov, df_resid=df_resid, rss=float(host[2 * k]),
-                        n_clusters=n_clusters, fe_dims=fe_dims, strategy="compress", iterations=0)
+                        n_clusters=n_clusters, fe_dims=fe_dims, strategy="compress", iterations=0, converged=converged,
+                        solver_sweeps=sweeps)

@@ -111,6 +111,8 @@ typedef int (*nccl_init_rank_fn)(void**, int, nccl_uid_t, int);
 typedef int (*nccl_destroy_fn)(void*);
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*nccl_errstr_fn)(int);
+typedef int (*nccl_sendrecv_fn)(void*, size_t, int, int, void*, cudaStream_t);   // ncclSend (const buf) / ncclRecv
+typedef int (*nccl_group_fn)(void);
 static struct {
   void* lib = nullptr;
   nccl_get_uid_fn get_uid = nullptr;
@@ -118,6 +120,8 @@ static struct {
   nccl_destroy_fn destroy = nullptr;
   nccl_allreduce_fn allreduce = nullptr;
   nccl_errstr_fn errstr = nullptr;
+  nccl_sendrecv_fn send = nullptr, recv = nullptr;
+  nccl_group_fn group_start = nullptr, group_end = nullptr;
 } g_nccl;
 enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
@@ -136,6 +140,10 @@ static void load_nccl() {
   g_nccl.destroy = (nccl_destroy_fn)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.allreduce = (nccl_allreduce_fn)dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.errstr = (nccl_errstr_fn)dlsym(g_nccl.lib, "ncclGetErrorString");
+  g_nccl.send = (nccl_sendrecv_fn)dlsym(g_nccl.lib, "ncclSend");
+  g_nccl.recv = (nccl_sendrecv_fn)dlsym(g_nccl.lib, "ncclRecv");
+  g_nccl.group_start = (nccl_group_fn)dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.group_end = (nccl_group_fn)dlsym(g_nccl.lib, "ncclGroupEnd");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy)
     LFE_THROW(LFE_ERR_NCCL, "libnccl is missing required symbols");
 }
@@ -147,14 +155,40 @@ static void load_nccl() {
 
 void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s) {
   if (h->world <= 1 || count <= 0) return;
+  h->n_collectives += 1;
   NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, NCCL_FLOAT64, op_max ? NCCL_MAX : NCCL_SUM, h->nccl_comm, s));
 }
 // kind: 0 = uint32, 1 = uint64, 2 = int64 ; op: 0 sum, 2 max, 3 min (NCCL numbering)
 void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s) {
   if (h->world <= 1 || count <= 0) return;
   const int nccl_type = kind == 0 ? 3 : (kind == 1 ? 5 : 4);
+  h->n_collectives += 1;
   NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, nccl_type, op, h->nccl_comm, s));
 }
+
+// all-to-all with per-peer byte counts: one grouped round of ncclSend / ncclRecv (self included)
+void comm_alltoallv_bytes(lfe_ctx* h, const void* send, const int64_t* send_off, const int64_t* send_cnt, void* recv,
+                          const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s) {
+  if (h->world <= 1) return;
+  if (!g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end)
+    LFE_THROW(LFE_ERR_NCCL, "libnccl has no ncclSend/ncclRecv (need NCCL >= 2.7)");
+  h->n_collectives += 1;
+  enum { NCCL_UINT8 = 1 };
+  NCCL_CHECK(g_nccl.group_start());
+  for (int r = 0; r < h->world; ++r) {
+    if (send_cnt[r] > 0)
+      NCCL_CHECK(g_nccl.send((void*)((const char*)send + send_off[r]), (size_t)send_cnt[r], NCCL_UINT8, r, h->nccl_comm, s));
+    if (recv_cnt[r] > 0)
+      NCCL_CHECK(g_nccl.recv((char*)recv + recv_off[r], (size_t)recv_cnt[r], NCCL_UINT8, r, h->nccl_comm, s));
+  }
+  NCCL_CHECK(g_nccl.group_end());
+}
+
+void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int64_t* cuts_out, int64_t* send_counts_out,
+                     int64_t* recv_counts_out, int32_t* order_out, cudaStream_t s);
+void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_counts, const int64_t* recv_counts,
+                         const void* const* cols_in, const int* dtypes, const int64_t* i32_sub, int K, int64_t n,
+                         void* const* cols_out, cudaStream_t s);
 
 // ---- exported functions -------------------------------------------------------------------------------
 extern "C" {
@@ -206,6 +240,7 @@ int lfe_reset_timers(lfe_handle h) {
   for (int i = 0; i < LFE_N_TIMERS; ++i) h->timer_ms[i] = 0.0;
   h->n_launches = 0;
   h->n_sweep_launches = 0;
+  h->n_collectives = 0;
   LFE_API_END
 }
 int lfe_get_timers(lfe_handle h, double* ms_out) {
@@ -218,7 +253,7 @@ int lfe_get_counters(lfe_handle h, int64_t* out) {
   LFE_API_BEGIN
   out[0] = h->n_launches;
   out[1] = h->n_sweep_launches;
-  out[2] = 0;
+  out[2] = h->n_collectives;
   out[3] = 0;
   LFE_API_END
 }
@@ -447,6 +482,26 @@ int lfe_comm_destroy(lfe_handle h) {
   h->world = 1;
   h->world_attached = 1;
   h->rank = 0;
+  LFE_API_END
+}
+int lfe_shard_plan(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_groups, int64_t* cuts_out,
+                   int64_t* send_counts_out, int64_t* recv_counts_out, int32_t* order_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && cuts_out && send_counts_out && recv_counts_out && (order_out || n == 0) && (codes || n == 0),
+              "lfe_shard_plan: NULL argument");
+  LFE_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, "lfe_shard_plan: n out of range");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  shard_plan_impl(h, codes, n, n_groups, cuts_out, send_counts_out, recv_counts_out, order_out, S(stream));
+  LFE_API_END
+}
+int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_counts, const int64_t* recv_counts,
+                       const void* const* cols_in, const int* dtypes, const int64_t* i32_sub, int K, int64_t n,
+                       void* const* cols_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && send_counts && recv_counts && (K == 0 || (cols_in && dtypes && cols_out)),
+              "lfe_shard_exchange: NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  shard_exchange_impl(h, order, send_counts, recv_counts, cols_in, dtypes, i32_sub, K, n, cols_out, S(stream));
   LFE_API_END
 }
 int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream) {

@@ -60,6 +60,7 @@ struct lfe_ctx {
   std::vector<cudaEvent_t> free_events;
   int64_t n_launches = 0;
   int64_t n_sweep_launches = 0;
+  int64_t n_collectives = 0;   // NCCL calls issued since the last timer reset
   // NCCL (dlopen'ed)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

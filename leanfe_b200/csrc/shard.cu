@@ -1,0 +1,189 @@
+// shard.cu -- multi-GPU row repartition: arbitrary row shards in, rows of each shard-key group on ONE rank out.
+//
+// No reference counterpart: the reference is a single process and evaluates the singleton filter and the FE
+// order on the whole frame (python/leanfe/polars_impl.py:478-485).  To reproduce that with rows spread over
+// the GPUs of a box, SURVEY 8(e) shards the rows by the highest-cardinality FE.  Here the library does it:
+//
+//   lfe_shard_plan      codes of the shard key come from ONE code space (lfe_factorize | LFE_ORDER_GLOBAL);
+//                       group sizes are counted per rank and all-reduced, the code axis is cut into `world`
+//                       contiguous ranges balanced by ROW count (a single-CTA 64-bit prefix walk -- the table is
+//                       at most a few MB and sits in L2), every row gets its destination rank, and a stable
+//                       8-bit radix argsort by destination gives the send order.
+//   lfe_shard_exchange  per column: gather into send order, one grouped ncclSend/ncclRecv round (all-to-all over
+//                       NVLink, self-copy included), optional re-basing of the shard key's codes to the local
+//                       range.  Rows arrive ordered by (source rank, original position).
+#include "common.cuh"
+
+void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);   // api.cu
+void comm_alltoallv_bytes(lfe_ctx* h, const void* send, const int64_t* send_off, const int64_t* send_cnt, void* recv,
+                          const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s);          // api.cu
+
+constexpr int SHARD_MAX_WORLD = 256;
+constexpr int CUT_T = 1024;
+
+// cuts[r] .. cuts[r+1]: code range of rank r; the rule of leanfe_b200/sharding.py:key_range_cuts
+// (first code whose inclusive row prefix reaches r * total / world, plus one), evaluated by one CTA
+__global__ void __launch_bounds__(CUT_T) k_balanced_cuts(const uint32_t* __restrict__ counts, int64_t G, int world,
+                                                         long long* __restrict__ cuts) {
+  __shared__ unsigned long long part[CUT_T];
+  __shared__ unsigned long long total_s;
+  const int t = threadIdx.x;
+  const int64_t chunk = ceil_div64(G, CUT_T);
+  const int64_t a = (int64_t)t * chunk, b = a + chunk < G ? a + chunk : G;
+  unsigned long long sum = 0;
+  for (int64_t g = a; g < b; ++g) sum += counts[g];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < CUT_T; ++i) { const unsigned long long v = part[i]; part[i] = run; run += v; }
+    total_s = run;
+    cuts[0] = 0;
+    cuts[world] = G;
+    for (int r = 1; r < world; ++r) cuts[r] = G;   // overwritten below unless the target is never reached (G == 0)
+  }
+  __syncthreads();
+  if (a >= b) return;
+  const unsigned long long total = total_s, excl = part[t], incl = excl + sum;
+  for (int r = 1; r < world; ++r) {
+    const unsigned long long target = (unsigned long long)r * total / (unsigned long long)world;
+    if ((t == 0 || excl < target) && incl >= target) {
+      unsigned long long c = excl;
+      for (int64_t g = a; g < b; ++g) {
+        c += counts[g];
+        if (c >= target) { cuts[r] = g + 1 < G ? g + 1 : G; break; }
+      }
+    }
+  }
+}
+
+// dest[i] = rank owning code[i] = number of inner cuts <= code; hist[r] += rows for rank r
+__global__ void __launch_bounds__(256) k_dest_rank(const int32_t* __restrict__ code, int64_t n,
+                                                   const long long* __restrict__ cuts, int world,
+                                                   uint32_t* __restrict__ dest, unsigned long long* __restrict__ hist) {
+  __shared__ long long sc[SHARD_MAX_WORLD + 1];
+  __shared__ unsigned int sh[SHARD_MAX_WORLD];
+  for (int i = threadIdx.x; i <= world; i += blockDim.x) sc[i] = cuts[i];
+  for (int i = threadIdx.x; i < world; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long c = __ldcs(code + i);
+    int lo = 1, hi = world;   // first r in [1, world) with cuts[r] > c, else world
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sc[mid] > c) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t r = (uint32_t)(lo - 1);
+    __stcs(dest + i, r);
+    atomicAdd(&sh[r], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < world; i += blockDim.x)
+    if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_by(const T* __restrict__ src, const uint32_t* __restrict__ order,
+                                                   int64_t n, T* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    __stcs(dst + i, __ldg(src + __ldcs(order + i)));
+}
+
+__global__ void __launch_bounds__(256) k_sub_i32(int32_t* __restrict__ p, int64_t n, int32_t sub) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] -= sub;
+}
+
+void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int64_t* cuts_out, int64_t* send_counts_out,
+                     int64_t* recv_counts_out, int32_t* order_out, cudaStream_t s) {
+  const int world = h->world, rank = h->rank;
+  LFE_REQUIRE(world <= SHARD_MAX_WORLD, "lfe_shard_plan: world %d exceeds %d", world, SHARD_MAX_WORLD);
+  LFE_REQUIRE(G >= 0 && G < (int64_t)0x7fffffff, "lfe_shard_plan: n_groups out of range");
+  PhaseTimer t(h, s, 14);
+  if (world == 1) {
+    cuts_out[0] = 0; cuts_out[1] = G;
+    send_counts_out[0] = n; recv_counts_out[0] = n;
+    if (n > 0) prim_iota_u32((uint32_t*)order_out, n, s);
+    return;
+  }
+  DevBuf<uint32_t> counts(G > 0 ? G : 1, s);
+  counts.zero();
+  if (n > 0 && G > 0) prim_histogram(h, codes, n, G, counts, s);
+  comm_allreduce_int(h, counts.p, G, 0, 0, s);
+  DevBuf<long long> cuts(world + 1, s);
+  k_balanced_cuts<<<1, CUT_T, 0, s>>>(counts, G, world, cuts);
+  KERNEL_CHECK();
+  DevBuf<unsigned long long> mat((size_t)world * world, s);   // mat[src][dst] = rows src sends to dst
+  mat.zero();
+  DevBuf<uint32_t> dest(n > 0 ? n : 1, s);
+  if (n > 0) {
+    k_dest_rank<<<launch_blocks(h, ceil_div64(n, 256 * 8), 8), 256, 0, s>>>(codes, n, cuts, world, dest,
+                                                                           mat.p + (size_t)rank * world);
+    KERNEL_CHECK();
+    prim_argsort_u32(h, dest, n, bits_for((uint64_t)(world - 1)), (uint32_t*)order_out, nullptr, s);
+  }
+  h->n_launches += 2;
+  comm_allreduce_int(h, mat.p, (int64_t)world * world, 1, 0, s);
+  std::vector<unsigned long long> hm((size_t)world * world);
+  std::vector<long long> hc(world + 1);
+  CUDA_CHECK(cudaMemcpyAsync(hm.data(), mat.p, hm.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(hc.data(), cuts.p, hc.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int r = 0; r <= world; ++r) cuts_out[r] = hc[r];
+  for (int r = 0; r < world; ++r) {
+    send_counts_out[r] = (int64_t)hm[(size_t)rank * world + r];
+    recv_counts_out[r] = (int64_t)hm[(size_t)r * world + rank];
+  }
+}
+
+static size_t dtype_size(int dt) {
+  switch (dt) {
+    case LFE_F64: case LFE_I64: case LFE_U64: return 8;
+    case LFE_I32: case LFE_U32: return 4;
+    case LFE_U8: return 1;
+    default: LFE_THROW(LFE_ERR_ARG, "lfe_shard_exchange: bad dtype %d", dt);
+  }
+}
+
+void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_counts, const int64_t* recv_counts,
+                         const void* const* cols_in, const int* dtypes, const int64_t* i32_sub, int K, int64_t n,
+                         void* const* cols_out, cudaStream_t s) {
+  const int world = h->world;
+  PhaseTimer t(h, s, 14);
+  int64_t n_recv = 0, n_send = 0;
+  std::vector<int64_t> soff(world), roff(world), sb(world), rb(world), sbo(world), rbo(world);
+  for (int r = 0; r < world; ++r) { soff[r] = n_send; n_send += send_counts[r]; roff[r] = n_recv; n_recv += recv_counts[r]; }
+  LFE_REQUIRE(n_send == n, "lfe_shard_exchange: send_counts sum to %lld, n = %lld", (long long)n_send, (long long)n);
+  size_t max_es = 1;
+  for (int c = 0; c < K; ++c) max_es = dtype_size(dtypes[c]) > max_es ? dtype_size(dtypes[c]) : max_es;
+  DevBuf<unsigned char> stage(world > 1 ? (size_t)(n > 0 ? n : 1) * max_es : 0, s);
+  const int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 8);
+  for (int c = 0; c < K; ++c) {
+    const size_t es = dtype_size(dtypes[c]);
+    if (world == 1) {
+      if (n > 0 && cols_out[c] != cols_in[c])
+        CUDA_CHECK(cudaMemcpyAsync(cols_out[c], cols_in[c], (size_t)n * es, cudaMemcpyDeviceToDevice, s));
+    } else {
+      if (n > 0) {
+        const uint32_t* ord = (const uint32_t*)order;
+        if (es == 8) k_gather_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, (uint64_t*)stage.p);
+        else if (es == 4) k_gather_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, (uint32_t*)stage.p);
+        else k_gather_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, (uint8_t*)stage.p);
+        KERNEL_CHECK();
+        h->n_launches += 1;
+      }
+      for (int r = 0; r < world; ++r) {
+        sbo[r] = soff[r] * (int64_t)es; sb[r] = send_counts[r] * (int64_t)es;
+        rbo[r] = roff[r] * (int64_t)es; rb[r] = recv_counts[r] * (int64_t)es;
+      }
+      comm_alltoallv_bytes(h, stage.p, sbo.data(), sb.data(), cols_out[c], rbo.data(), rb.data(), s);
+    }
+    if (i32_sub && i32_sub[c] != 0 && n_recv > 0) {
+      LFE_REQUIRE(dtypes[c] == LFE_I32, "lfe_shard_exchange: i32_sub on a non-int32 column");
+      k_sub_i32<<<launch_blocks(h, ceil_div64(n_recv, 256 * 8), 8), 256, 0, s>>>((int32_t*)cols_out[c], n_recv,
+                                                                                (int32_t)i32_sub[c]);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
+  }
+}

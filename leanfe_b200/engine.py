@@ -88,12 +88,12 @@ class Engine:
     def timers(self) -> dict:
         out = (C.c_double * capi.N_TIMERS)()
         capi.check(self.lib.lfe_get_timers(self.h, out))
-        return {capi.TIMER_NAMES[i]: out[i] for i in range(14)}
+        return {capi.TIMER_NAMES[i]: out[i] for i in range(15)}
 
     def counters(self) -> dict:
         out = (C.c_int64 * 4)()
         capi.check(self.lib.lfe_get_counters(self.h, out))
-        return {"launches": out[0], "sweep_launches": out[1]}
+        return {"launches": out[0], "sweep_launches": out[1], "collectives": out[2]}
 
     # -- (1) group codes ----------------------------------------------------------------------
     def factorize(self, keys: torch.Tensor, order: int = capi.ORDER_SORTED, want_uniques: bool = False,
@@ -111,11 +111,14 @@ class Engine:
             cap = n if uniques_cap is None else min(n, int(uniques_cap))
             if order & capi.ORDER_GLOBAL and self.world > 1:
                 cap = int(uniques_cap or (1 << 20))     # the shared code space may hold keys this rank never sees
+            cap = max(cap, 1)
             uniq = self.empty(cap, keys.dtype)
         rc = self.lib.lfe_factorize(self.h, self._p(keys), _TORCH_TO_LFE[keys.dtype], n, order, self._p(codes),
                                     C.byref(G), self._p(uniq), cap, self.stream)
-        if rc == capi.ERR_CAPACITY and want_uniques and cap < n and not (order & capi.ORDER_GLOBAL and self.world > 1):
-            return self.factorize(keys, order, True, n)
+        if rc == capi.ERR_CAPACITY and want_uniques and cap < int(G.value):
+            # n_groups_out is filled even when the uniques did not fit: retry once with exactly that capacity (in the
+            # shared code space of a multi-GPU fit G may exceed this rank's row count)
+            return self.factorize(keys, order, True, int(G.value))
         capi.check(rc)
         return codes, int(G.value), (uniq[: G.value] if uniq is not None else None)
 
@@ -335,6 +338,35 @@ class Engine:
     def allreduce(self, t: torch.Tensor):
         capi.check(self.lib.lfe_allreduce_f64(self.h, self._p(t), t.numel(), self.stream))
         return t
+
+    def shard_plan(self, codes: torch.Tensor, n_groups: int):
+        """lfe_shard_plan: balanced code-range cuts of the shard key + this rank's send order.
+        -> dict(cuts, send_counts, recv_counts, order)"""
+        self._check_dev(codes)
+        n, W = codes.numel(), self.world
+        cuts, sc, rc = (C.c_int64 * (W + 1))(), (C.c_int64 * W)(), (C.c_int64 * W)()
+        order = self.empty(n, torch.int32)
+        capi.check(self.lib.lfe_shard_plan(self.h, self._p(codes), n, int(n_groups), cuts, sc, rc, self._p(order),
+                                           self.stream))
+        return dict(cuts=[int(c) for c in cuts], send_counts=[int(c) for c in sc], recv_counts=[int(c) for c in rc],
+                    order=order)
+
+    def shard_exchange(self, plan: dict, cols: list[torch.Tensor], i32_sub: list[int] | None = None):
+        """lfe_shard_exchange: all-to-all of the columns by the plan's destination ranks.  -> new tensors holding
+        the rows this rank owns (ordered by source rank, original order inside each source)."""
+        self._check_dev(*cols)
+        n = plan["order"].numel()
+        n_recv = sum(plan["recv_counts"])
+        for t in cols:
+            if t.numel() != n or t.dtype not in _TORCH_TO_LFE:
+                raise ValueError("shard_exchange: columns must have one value per planned row (int32/int64/uint8/float64)")
+        out = [self.empty(n_recv, t.dtype) for t in cols]
+        capi.check(self.lib.lfe_shard_exchange(
+            self.h, self._p(plan["order"]), capi.i64_array(plan["send_counts"]), capi.i64_array(plan["recv_counts"]),
+            capi.ptr_array([t.data_ptr() for t in cols]), capi.i32_array([_TORCH_TO_LFE[t.dtype] for t in cols]),
+            capi.i64_array(i32_sub) if i32_sub is not None else None, len(cols), n,
+            capi.ptr_array([t.data_ptr() for t in out]), self.stream))
+        return out
 
     def key_ranges(self, cols: list[torch.Tensor]):
         """lfe_key_ranges: -> [(min, max)] of integer columns (uint8 / int32 / int64), one pass each, one sync;

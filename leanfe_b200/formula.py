@@ -7,7 +7,7 @@ Behaviour mirrors ``parse_formula`` in the reference (python/leanfe/common.py:51
     y ~ x1 + i(region)                factor dummies, first sorted level is the reference
     y ~ x1 + i(region, ref=R1)        explicit reference level (quotes optional)
     y ~ x1 + treat:i(region)          heterogeneous slopes
-    y ~ x1 | fe1 | z1 + z2            third part = instruments (IV; parsed, not estimated here)
+    y ~ x1 | fe1 | z1 + z2            third part = instruments (IV/2SLS, estimated by api._regress_iv)
 """
 from __future__ import annotations
 

@@ -4,7 +4,7 @@ Contract (reference python/leanfe/result.py:11-296): attributes ``coefs``, ``std
 ``p_values``, ``n_obs``, ``iterations``, ``n_compressed``, ``compression_ratio``, ``vcov_type``, ``is_iv``,
 ``n_instruments``, ``n_clusters``, ``df_resid``, ``r_squared``, ``r_squared_within``, ``rss``, ``tss``,
 ``formula``, ``fe_cols``, ``fe_dims``; printable table; ``coef/se/tstat/pvalue/confint``; dict-like access
-over ``to_dict()``.  Supersets (harmless to reference users): ``strategy``, ``converged``, ``timings``; the
+over ``to_dict()``.  Supersets (harmless to reference users): ``strategy``, ``converged``, ``timings``, ``solver_sweeps``; the
 ``"coefficients"`` key is accepted as an alias of ``"coefs"`` (the reference's docs/tests still use it);
 ``_vcov_description`` no longer breaks on multi-way cluster tuples.
 """
@@ -41,7 +41,7 @@ class LeanFEResult:
     def __init__(self, coefs, std_errors, n_obs, vcov_type, iterations=0, n_compressed=None, compression_ratio=None,
                  is_iv=False, n_instruments=None, n_clusters=None, df_resid=None, r_squared=None,
                  r_squared_within=None, rss=None, tss=None, formula=None, fe_cols=None, fe_dims=None,
-                 strategy=None, converged=None, timings=None):
+                 strategy=None, converged=None, timings=None, solver_sweeps=None):
         self.coefs = coefs
         self.std_errors = std_errors
         self.n_obs = n_obs
@@ -63,6 +63,7 @@ class LeanFEResult:
         self.strategy = strategy
         self.converged = converged
         self.timings = timings
+        self.solver_sweeps = solver_sweeps   # strategy='compress': sweeps of the weighted FWL solve (iterations stays 0)
         self.t_stats, self.p_values = {}, {}
         for name, b in coefs.items():
             s = std_errors[name]

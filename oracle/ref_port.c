@@ -176,7 +176,11 @@ int lfe_port_fit(const double* const* cols_in, int k, const int64_t* const* fe_k
   memset(keep, 1, (size_t)n0);
   for (int j = 0; j < F; ++j) {
     int32_t* cnt = (int32_t*)calloc((size_t)G[j], sizeof(int32_t));
-    for (int64_t i = 0; i < n0; ++i) cnt[code0[j][i]]++;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n0; ++i) {
+#pragma omp atomic
+      cnt[code0[j][i]]++;
+    }
 #pragma omp parallel for
     for (int64_t i = 0; i < n0; ++i)
       if (cnt[code0[j][i]] <= 1) keep[i] = 0;
@@ -184,7 +188,26 @@ int lfe_port_fit(const double* const* cols_in, int k, const int64_t* const* fe_k
   }
   int64_t n = 0;
   int64_t* pos = (int64_t*)malloc((size_t)n0 * sizeof(int64_t));
-  for (int64_t i = 0; i < n0; ++i) { pos[i] = n; n += keep[i]; }
+  {
+    /* exclusive prefix sum of keep[] in two parallel passes over per-thread blocks */
+    const int T = omp_get_max_threads();
+    int64_t* part = (int64_t*)calloc((size_t)T + 1, sizeof(int64_t));
+    const int64_t blk = (n0 + T - 1) / T;
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+      int64_t a = t * blk, b = a + blk < n0 ? a + blk : n0, c = 0;
+      for (int64_t i = a; i < b; ++i) c += keep[i];
+      part[t + 1] = c;
+    }
+    for (int t = 0; t < T; ++t) part[t + 1] += part[t];
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+      int64_t a = t * blk, b = a + blk < n0 ? a + blk : n0, c = part[t];
+      for (int64_t i = a; i < b; ++i) { pos[i] = c; c += keep[i]; }
+    }
+    n = part[T];
+    free(part);
+  }
   double* cols[MAXC];
   int32_t* code[MAXF];
   for (int c = 0; c < C; ++c) {
@@ -202,7 +225,11 @@ int lfe_port_fit(const double* const* cols_in, int k, const int64_t* const* fe_k
       if (keep[i]) code[j][pos[i]] = code0[j][i];
     free(code0[j]);
     cnt[j] = (double*)calloc((size_t)G[j], sizeof(double));
-    for (int64_t i = 0; i < n; ++i) cnt[j][code[j][i]] += 1.0;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) {
+#pragma omp atomic
+      cnt[j][code[j][i]] += 1.0;
+    }
     for (int64_t g = 0; g < G[j]; ++g) fe_dims += cnt[j][g] > 0;
   }
   int32_t* cl = NULL;
@@ -312,6 +339,7 @@ int lfe_port_fit(const double* const* cols_in, int k, const int64_t* const* fe_k
         }
       }
       uint8_t* seen = (uint8_t*)calloc((size_t)Gcl, 1);
+#pragma omp parallel for
       for (int64_t i = 0; i < n; ++i) seen[cl[i]] = 1;
       for (int64_t g = 0; g < Gcl; ++g) {
         n_clusters += seen[g];
@@ -347,3 +375,6 @@ int lfe_port_fit(const double* const* cols_in, int k, const int64_t* const* fe_k
 }
 
 int lfe_port_threads(void) { return omp_get_max_threads(); }
+
+/* bench.py sets the thread count explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers */
+void lfe_port_set_threads(int t) { if (t > 0) omp_set_num_threads(t); }

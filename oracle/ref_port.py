@@ -30,6 +30,12 @@ def threads() -> int:
     return int(_load().lfe_port_threads())
 
 
+def set_threads(t: int) -> int:
+    """Use ``t`` OpenMP threads from now on (overrides an inherited OMP_NUM_THREADS); -> the count in effect."""
+    _load().lfe_port_set_threads(C.c_int(int(t)))
+    return threads()
+
+
 def fit(y, X: list, fe: list, cluster=None, tol=1e-6, max_iter=50, vcov="iid", ssc=True):
     """alt_proj fit on all host cores.  X: list of float64 arrays, fe: list of int64 id arrays."""
     lib = _load()

@@ -16,20 +16,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run_checks(rank: int, world: int) -> list:
+    """All parity panels against the single-process oracle; needs torch.distributed (nccl) initialised and the
+    engine's communicator attached.  -> list of failure records (empty = parity green).  Also called by bench.py
+    before the timed region of every multi-GPU run (`mg_parity`)."""
     import torch
     import torch.distributed as dist
 
     from leanfe_b200 import leanfe
-    from leanfe_b200.engine import get_engine
     from leanfe_b200.sharding import shard_rows_by_key
     from oracle import ref_numpy as O
-
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    eng = get_engine(local)
-    eng.comm_init_from_torch()
 
     rng = np.random.default_rng(123)                      # same panel on every rank
     N, G1, G2 = 600_000, 12_000, 60
@@ -63,6 +59,29 @@ def main():
         if not ok:
             failures.append((vc, cl, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs, ref["n_obs"],
                              res.fe_dims, ref["fe_dims"], res.n_clusters, ref["n_clusters"]))
+    # ARBITRARY row shards (no local_fe): the library repartitions by the highest-cardinality FE itself
+    # (lfe_shard_plan / lfe_shard_exchange); shard sizes are deliberately unequal (rank 0 holds a third of its share)
+    owner = (np.arange(N) * 7919) % world
+    owner[(owner == 0) & (rng.random(N) < 0.67)] = world - 1
+    mine_a = np.flatnonzero(owner == rank)
+    shard_a = {k: v[mine_a] for k, v in full.items()}
+    for vc, cl in (("iid", None), ("cluster", ["unit"]), ("cluster", ["time"])):
+        kw = dict(formula="y ~ x1 + x2 | unit + time", vcov=vc, cluster_cols=cl, strategy="alt_proj")
+        res = leanfe(shard_a, **kw)
+        ref = O.leanfe_oracle(full, **kw)
+        b, eb = np.array(list(res.coefs.values())), np.array(list(ref["coefs"].values()))
+        s, es = np.array(list(res.std_errors.values())), np.array(list(ref["std_errors"].values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.iterations == ref["iterations"] and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and tuple(res.fe_dims) == tuple(ref["fe_dims"]) and res.n_clusters == ref["n_clusters"])
+        t = torch.tensor(list(b) + list(s), dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and bool(torch.equal(lo, hi))
+        if not ok:
+            failures.append(("arbitrary-shards", vc, cl, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs,
+                             ref["n_obs"], res.fe_dims, ref["fe_dims"], res.n_clusters, ref["n_clusters"]))
     # three-way FE (worker = shard key, firm and year shared by all ranks), weighted, max_iter reached
     nw, nf = 9000, 700
     worker = rng.integers(0, nw, N)
@@ -87,6 +106,17 @@ def main():
         if not ok:
             failures.append(("3way", vc, cl, wname, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs,
                              ref["n_obs"], res.fe_dims, ref["fe_dims"]))
+        # the same fit from round-robin row shards, repartitioned by the library (weights travel with the rows)
+        shard3a = {k: v[rank::world] for k, v in full3.items()}
+        res = leanfe(shard3a, **kw)
+        b = np.array(list(res.coefs.values()))
+        s = np.array(list(res.std_errors.values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.iterations == ref["iterations"] and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and tuple(res.fe_dims) == tuple(ref["fe_dims"]) and res.n_clusters == ref["n_clusters"])
+        if not ok:
+            failures.append(("3way-arbitrary-shards", vc, cl, wname, b, eb, s, es, res.iterations, ref["iterations"],
+                             res.n_obs, ref["n_obs"], res.fe_dims, ref["fe_dims"]))
     # YOCO (strategy='compress'): rows sharded ARBITRARILY (round-robin), every key spans ranks; one dummy is
     # non-zero on rank 0's rows only, one period exists on rank 1's rows only (shared code space needed)
     Ny, ng, npd = 400_000, 150, 10
@@ -121,6 +151,21 @@ def main():
         if not ok:
             failures.append(("yoco", vc, cl, wname, b, eb, s, es, res.n_obs, ref["n_obs"], res.df_resid, ref["df_resid"],
                              res.n_compressed, ref["n_compressed"], res.n_clusters, ref["n_clusters"]))
+    return failures
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from leanfe_b200.engine import get_engine
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = get_engine(local)
+    eng.comm_init_from_torch()
+    failures = run_checks(rank, world)
     if rank == 0:
         print("multigpu_check:", "OK" if not failures else f"FAILED {failures}", f"(world={world})")
     dist.destroy_process_group()
