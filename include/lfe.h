@@ -163,6 +163,20 @@ int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols,
                         int C, const int* fe_order,
                         double tol, int max_iter, int min_iter, int flags, int* iterations_out /*[host]*/,
                         double* max_mean_out /*[host]*/, int* converged_out /*[host]*/, void* stream);
+/* The whole fit after the plan, in one call and WITHOUT materialising the demeaned columns: sweeps as in
+ * lfe_demean_plan_run, then -- x~_i = x_i - sum_j alpha_j[code_j(i)] formed in registers from the raw columns and
+ * the converged FE tables -- the [1 | X~] normal equations and their Cholesky solve (polars_impl.py:166-226), the
+ * residual statistics (:229-283) and the IID / HC1 / one-way clustered sandwich (std_errors.py:183-347).  Replaces
+ * lfe_demean_plan_run + lfe_gram + lfe_solve_spd + lfe_resid_vcov for C = 1 + k <= 11 columns; cols (cols[0] = y)
+ * are read-only.  vcov_kind as in lfe_resid_vcov (cl_codes: ONE code column in row order, or NULL).
+ * Outputs (device): beta_full_out (k + 1, intercept first), se_out (k), vcov_out (k x k, nullable), stats_out
+ * (4: rss, tss, sum w r^2, 0).  Synchronises `stream`.                                                   */
+int lfe_demean_plan_fit(lfe_handle h, lfe_plan_t plan, const double* const* cols, int C, const int* fe_order,
+                        double tol, int max_iter, int min_iter, int flags, int vcov_kind, const int32_t* cl_codes,
+                        int64_t n_cl_groups, int ssc, int64_t n_obs, int64_t df_resid, double* beta_full_out,
+                        double* se_out, double* vcov_out, double* stats_out, int* iterations_out /*[host]*/,
+                        double* max_mean_out /*[host]*/, int* converged_out /*[host]*/,
+                        int64_t* n_clusters_out /*[host], nullable*/, void* stream);
 int lfe_demean_plan_destroy(lfe_handle h, lfe_plan_t plan);
 
 /* ---- (4) Gram + solve --------------------------------------------------------------------------

@@ -26,7 +26,7 @@ EXPORTS = [
     "lfe_version", "lfe_last_error", "lfe_create", "lfe_destroy", "lfe_set_profiling", "lfe_reset_timers",
     "lfe_get_timers", "lfe_get_counters", "lfe_factorize", "lfe_factorize_counts", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
     "lfe_sort_rows", "lfe_gather", "lfe_demean", "lfe_demean_plan_create", "lfe_demean_plan_run",
-    "lfe_demean_plan_destroy", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
+    "lfe_demean_plan_destroy", "lfe_demean_plan_fit", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
     "lfe_allreduce_f64", "lfe_shard_plan", "lfe_shard_exchange",
 ]
@@ -73,6 +73,8 @@ def load_library() -> C.CDLL:
     lib.lfe_demean_plan_create.argtypes = [vp, P(vp), P(i64), i32, i64, vp, i32, P(vp), P(vp), vp]
     lib.lfe_demean_plan_run.argtypes = [vp, vp, P(vp), P(vp), i32, P(i32), dbl, i32, i32, i32, P(i32), P(dbl), P(i32), vp]
     lib.lfe_demean_plan_destroy.argtypes = [vp, vp]
+    lib.lfe_demean_plan_fit.argtypes = [vp, vp, P(vp), i32, P(i32), dbl, i32, i32, i32, i32, vp, i64, i32, i64, i64,
+                                        vp, vp, vp, vp, P(i32), P(dbl), P(i32), P(i64), vp]
     lib.lfe_gram.argtypes = [vp, P(vp), i32, i64, vp, i32, vp, vp]
     lib.lfe_solve_spd.argtypes = [vp, vp, vp, i32, vp, vp, P(i32), vp]
     lib.lfe_resid_vcov.argtypes = [vp, P(vp), i32, i64, vp, vp, i32, P(vp), P(i64), i32, vp, i32, i64, i64,

@@ -387,6 +387,35 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
             if cols is None:
                 y, X, x_cols, w = get_columns()
                 k = len(X)
+                raw = [y] + X
+            else:
+                raw = cols
+            kind = vkind & 0xFF
+            if (iv is None and len(raw) <= plan.FIT_MAX_COLS and (kind != capi.VCOV_CLUSTER or len(cl_codes) == 1)
+                    and all(t.dtype == torch.float64 and t.is_contiguous() for t in raw)):
+                # the usual fit: one library call, the demeaned columns are formed in registers and never written
+                # (lfe_demean_plan_fit); df_resid needs only fe_dims, known since the singleton pass
+                absorbed = (fe_dims[0] - 1) if strategy == "demean" else (sum(fe_dims) - F)
+                p = k + 1
+                df_resid = n_obs - p - absorbed
+                if kind == capi.VCOV_CLUSTER and cl_local:
+                    vkind |= capi.VCOV_CLUSTER_LOCAL
+                mi, mn = (1, 2) if strategy == "demean" else (max_iter, 3)
+                out = plan.fit(raw, order, tol, mi, mn, vkind, cl_codes[0] if kind == capi.VCOV_CLUSTER else None,
+                               cl_keys[0].n_groups if kind == capi.VCOV_CLUSTER else 0, ssc, n_obs, df_resid)
+                plan.close()
+                iterations, converged = (1, True) if strategy == "demean" else (out["iterations"], out["converged"])
+                host = out["packed"].cpu().numpy()
+                beta, se = host[1:p], host[p:p + k]
+                rss, tss = host[-4], host[-3]
+                n_clusters = out["n_clusters"] if kind == capi.VCOV_CLUSTER else None
+                r2 = float(1 - rss / tss) if tss > 0 else None
+                return LeanFEResult(coefs=dict(zip(x_cols, beta.tolist())), std_errors=dict(zip(x_cols, se.tolist())),
+                                    n_obs=n_obs, iterations=iterations, vcov_type=vcov, is_iv=False, n_instruments=None,
+                                    n_clusters=n_clusters, df_resid=df_resid, formula=formula, fe_cols=fe_cols,
+                                    fe_dims=fe_dims, r_squared=r2, compression_ratio=est_ratio, rss=float(rss),
+                                    tss=float(tss), strategy=strategy, converged=converged)
+            if cols is None:
                 own = getattr(get_columns, "owned", lambda t: False)
                 src = [y] + X
                 # caller-owned device columns are read in place and the demeaned values written to fresh buffers

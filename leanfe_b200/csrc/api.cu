@@ -25,6 +25,11 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
                      const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
                      double* max_mean_out, int* converged_out, cudaStream_t s);
 void demean_plan_destroy(lfe_plan* plan);
+void demean_plan_fit(lfe_ctx* h, lfe_plan* plan, const double* const* cols, int C, const int* fe_order, double tol,
+                     int max_iter, int min_iter, int flags, int vcov_kind, const int32_t* cl_codes, int64_t n_cl_groups,
+                     int ssc, int64_t n_obs, int64_t df_resid, double* beta_full_out, double* se_out, double* vcov_out,
+                     double* stats_out, int* iterations_out, double* max_mean_out, int* converged_out,
+                     int64_t* n_clusters_out, cudaStream_t s);
 void gram_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* weights, int add_intercept,
                double* gram_out, cudaStream_t s);
 void solve_spd_impl(lfe_ctx* h, const double* A, const double* b, int p, double* beta_out, double* Ainv_out,
@@ -363,6 +368,23 @@ int lfe_demean_plan_run(lfe_handle h, lfe_plan_t plan, double* const* cols, cons
   CUDA_CHECK(cudaSetDevice(h->device));
   demean_plan_run(h, plan, cols, cols_src, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
                   converged_out, S(stream));
+  LFE_API_END
+}
+int lfe_demean_plan_fit(lfe_handle h, lfe_plan_t plan, const double* const* cols, int C, const int* fe_order, double tol,
+                        int max_iter, int min_iter, int flags, int vcov_kind, const int32_t* cl_codes, int64_t n_cl_groups,
+                        int ssc, int64_t n_obs, int64_t df_resid, double* beta_full_out, double* se_out, double* vcov_out,
+                        double* stats_out, int* iterations_out, double* max_mean_out, int* converged_out,
+                        int64_t* n_clusters_out, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && plan && cols && fe_order && iterations_out && beta_full_out && (C == 1 || se_out),
+              "lfe_demean_plan_fit: NULL argument");
+  const int kind = vcov_kind & ~LFE_VCOV_CLUSTER_LOCAL;
+  LFE_REQUIRE(kind >= 0 && kind <= 2, "lfe_demean_plan_fit: unknown vcov kind %d", kind);
+  LFE_REQUIRE(kind != LFE_VCOV_CLUSTER || (cl_codes && n_cl_groups >= 1), "lfe_demean_plan_fit: cluster codes required");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  demean_plan_fit(h, plan, cols, C, fe_order, tol, max_iter, min_iter, flags, vcov_kind, cl_codes, n_cl_groups, ssc, n_obs,
+                  df_resid, beta_full_out, se_out, vcov_out, stats_out, iterations_out, max_mean_out, converged_out,
+                  n_clusters_out, S(stream));
   LFE_API_END
 }
 int lfe_demean_plan_destroy(lfe_handle h, lfe_plan_t plan) {

@@ -22,7 +22,40 @@
 #include "common.cuh"
 #include "segreduce.cuh"
 
+#include "tail.cuh"
+
 void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);  // api.cu
+void gram_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* weights, const TailTabs& T,
+                     int ldc, size_t smem, double* gram_out, cudaStream_t s);                                   // gram.cu
+void solve_spd_impl(lfe_ctx* h, const double* A, const double* b, int p, double* beta_out, double* Ainv_out,
+                    int* used_fallback_out, cudaStream_t s);                                                    // gram.cu
+void resid_vcov_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const TailTabs& T, int ldc,
+                           size_t tab_smem, const double* beta_full, const double* Binv, int vcov_kind, const int32_t* cl,
+                           int64_t Gcap, const double* weights, int ssc, int64_t n_obs, int64_t df_resid, double* se_out,
+                           double* vcov_out, double* stats_out, int64_t* n_clusters_out, cudaStream_t s);       // vcov.cu
+
+// what lfe_demean_plan_fit wants done with the converged tables instead of applying them to the columns
+struct TailRequest {
+  int vcov_kind;
+  const int32_t* cl_codes;   // one-way cluster codes (row order), nullable
+  int64_t n_cl_groups;
+  int ssc;
+  int64_t n_obs, df_resid;
+  double *beta_full_out, *se_out, *vcov_out, *stats_out;   // device
+  int64_t* n_clusters_out;                                  // host
+};
+
+// A = G[0:p, 0:p], b = G[0:p, p]   (G is (p+1) x (p+1): order [1, x.., y])
+__global__ void k_split_gram(const double* __restrict__ G, int p, double* __restrict__ A, double* __restrict__ b) {
+  const int P = p + 1;
+  for (int i = threadIdx.x; i < p * p; i += blockDim.x) A[i] = G[(i / p) * P + (i % p)];
+  for (int i = threadIdx.x; i < p; i += blockDim.x) b[i] = G[i * P + p];
+}
+// B = Ainv[1:, 1:]
+__global__ void k_drop_intercept(const double* __restrict__ Ainv, int p, double* __restrict__ B) {
+  const int k = p - 1;
+  for (int i = threadIdx.x; i < k * k; i += blockDim.x) B[i] = Ainv[(i / k + 1) * p + (i % k + 1)];
+}
 
 // acc[key][acc_col0 + c] += w * sum_k alpha_k[code_k][col0 + c]    over the FE-sorted entry list
 constexpr int PJ_NB = 2;  // sub-batches of PJ_I entries per thread: 8 consecutive entries, one warp scan
@@ -1054,9 +1087,10 @@ void demean_plan_destroy(lfe_plan* plan) { delete plan; }
 
 // cols_src (nullable): read the input columns from there and write the demeaned columns to `cols`
 // (out of place: the caller's data stay untouched without a separate copy); nullptr = in place on `cols`.
-void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const double* const* cols_src, int C,
-                     const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
-                     double* max_mean_out, int* converged_out, cudaStream_t s) {
+static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols, const double* const* cols_src, int C,
+                                 const int* fe_order, double tol, int max_iter, int min_iter, int flags,
+                                 int* iterations_out, double* max_mean_out, int* converged_out, const TailRequest* tail,
+                                 cudaStream_t s) {
   std::vector<const double*> src_v(C);
   for (int c = 0; c < C; ++c) src_v[c] = cols_src ? cols_src[c] : cols[c];
   const double* const* in = src_v.data();
@@ -1291,6 +1325,36 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
     }
   }
 
+  *iterations_out = iterations;
+  if (max_mean_out) *max_mean_out = max_mean;
+  if (converged_out) *converged_out = converged ? 1 : 0;
+  if (tail) {
+    // ---- regression tail straight from (columns, tables): nothing is written back -------------------
+    TailTabs T;
+    int64_t rows[LFE_MAX_FE];
+    T.n = F;
+    for (int j = 0; j < F; ++j) {
+      T.code[j] = codes[j];
+      T.alpha[j] = st[j].alpha;
+      rows[j] = st[j].G;
+    }
+    const size_t tab_smem = plan_staging(T, rows, Cp);
+    const int p = C;   // intercept + k regressors
+    DevBuf<double> gram((size_t)(p + 1) * (p + 1), s), A((size_t)p * p, s), b(p, s), Ainv((size_t)p * p, s);
+    DevBuf<double> B((size_t)(p > 1 ? (p - 1) * (p - 1) : 1), s);
+    gram_fused_impl(h, in, C, n, weights, T, Cp, tab_smem, gram, s);
+    k_split_gram<<<1, 256, 0, s>>>(gram, p, A, b);
+    KERNEL_CHECK();
+    solve_spd_impl(h, A, b, p, tail->beta_full_out, Ainv, nullptr, s);
+    k_drop_intercept<<<1, 256, 0, s>>>(Ainv, p, B);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    resid_vcov_fused_impl(h, in, C, n, T, Cp, tab_smem, tail->beta_full_out, B, tail->vcov_kind, tail->cl_codes,
+                          tail->n_cl_groups, weights, tail->ssc, tail->n_obs, tail->df_resid, tail->se_out,
+                          tail->vcov_out, tail->stats_out, tail->n_clusters_out, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));   // B / Ainv scratch and the caller's host outputs
+    return;
+  }
   // ---- apply the tables to the columns, in place ------------------------------------------------
   {
     PhaseTimer t(h, s, 8);
@@ -1310,9 +1374,28 @@ void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const doub
       if (n > 0) launch_apply(h, nc, mp, T, n, Cp, c0, apply_smem, s);
     }
   }
-  *iterations_out = iterations;
-  if (max_mean_out) *max_mean_out = max_mean;
-  if (converged_out) *converged_out = converged ? 1 : 0;
+}
+
+void demean_plan_run(lfe_ctx* h, lfe_plan* plan, double* const* cols, const double* const* cols_src, int C,
+                     const int* fe_order, double tol, int max_iter, int min_iter, int flags, int* iterations_out,
+                     double* max_mean_out, int* converged_out, cudaStream_t s) {
+  demean_plan_run_tail(h, plan, cols, cols_src, C, fe_order, tol, max_iter, min_iter, flags, iterations_out, max_mean_out,
+                       converged_out, nullptr, s);
+}
+
+// lfe_demean_plan_fit: sweeps + [1 | X~] normal equations + solve + residual statistics + IID / HC1 / one-way
+// clustered SEs, with the demeaned columns formed on the fly (never written).  cols are read-only.
+void demean_plan_fit(lfe_ctx* h, lfe_plan* plan, const double* const* cols, int C, const int* fe_order, double tol,
+                     int max_iter, int min_iter, int flags, int vcov_kind, const int32_t* cl_codes, int64_t n_cl_groups,
+                     int ssc, int64_t n_obs, int64_t df_resid, double* beta_full_out, double* se_out, double* vcov_out,
+                     double* stats_out, int* iterations_out, double* max_mean_out, int* converged_out,
+                     int64_t* n_clusters_out, cudaStream_t s) {
+  LFE_REQUIRE(C >= 1 && C <= TL_MAXC, "lfe_demean_plan_fit: %d columns unsupported (max %d); use lfe_demean_plan_run + "
+              "lfe_gram + lfe_resid_vcov", C, TL_MAXC);
+  TailRequest tr{vcov_kind, cl_codes, n_cl_groups, ssc, n_obs, df_resid, beta_full_out, se_out, vcov_out, stats_out,
+                 n_clusters_out};
+  demean_plan_run_tail(h, plan, const_cast<double* const*>(cols), cols, C, fe_order,
+                       tol, max_iter, min_iter, flags, iterations_out, max_mean_out, converged_out, &tr, s);
 }
 
 void demean_impl(lfe_ctx* h, double* const* cols, int C, const int32_t* const* codes, const int64_t* n_groups,

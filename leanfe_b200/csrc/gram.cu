@@ -8,6 +8,7 @@
 // Block partials are reduced in a fixed order by a second kernel, so results are run-to-run
 // deterministic.
 #include "common.cuh"
+#include "tail.cuh"
 
 void comm_allreduce(lfe_ctx* h, double* buf, int64_t count, int op_max, cudaStream_t s);  // api.cu
 
@@ -204,6 +205,136 @@ void gram_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const do
     int P = C + (add_intercept ? 1 : 0);
     comm_allreduce(h, gram_out, (int64_t)P * P, 0, s);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram of the DEMEANED columns straight from (raw columns, FE tables): Z = [1 | x~_1..x~_k | y~] with
+// x~_i = x_i - sum_j alpha_j[code_j(i)] formed in registers (tail.cuh).  Replaces k_apply4 (write N x C) +
+// k_gram_tri (read N x C): N*(8C + 4F) bytes instead of N*(24C + 4F).
+// ---------------------------------------------------------------------------------------------
+template <int NC, int R, bool VEC, bool WEIGHTED>
+__global__ void __launch_bounds__(TL_T) k_tail_gram(TailCols cols, TailTabs T, const double* __restrict__ w, int64_t n,
+                                                    int ldc, double* __restrict__ partials) {
+  constexpr int P = NC + 1;
+  constexpr int NT = P * (P + 1) / 2;
+  extern __shared__ double sm_tabs[];
+  const double* tabs[LFE_MAX_FE];
+  stage_tables(T, ldc, sm_tabs, tabs);
+  const bool vec2 = (ldc & 1) == 0;
+  double acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+  const int64_t ngroups = VEC ? n / R : ceil_div64(n, R);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+    double x[R][NC];
+    bool valid[R];
+    tail_rows<NC, R, VEC>(cols, T, tabs, ldc, vec2, g * R, n, x, valid);
+    double om[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) om[r] = WEIGHTED ? (valid[r] ? __ldcs(w + g * R + r) : 0.0) : (valid[r] ? 1.0 : 0.0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double z[P];
+      z[0] = 1.0;
+#pragma unroll
+      for (int c = 1; c < NC; ++c) z[c] = x[r][c];
+      z[P - 1] = x[r][0];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < P; ++a) {
+        const double za = z[a] * om[r];
+#pragma unroll
+        for (int b = a; b < P; ++b) {
+          acc[t] = fma(za, z[b], acc[t]);
+          ++t;
+        }
+      }
+    }
+  }
+  if (VEC && blockIdx.x == 0 && threadIdx.x < (int)(n % R)) {   // the last n % R rows
+    double x[1][NC];
+    bool valid[1];
+    const int64_t i = (n / R) * R + threadIdx.x;
+    tail_rows<NC, 1, false>(cols, T, tabs, ldc, vec2, i, n, x, valid);
+    const double om = WEIGHTED ? w[i] : 1.0;
+    double z[P];
+    z[0] = 1.0;
+#pragma unroll
+    for (int c = 1; c < NC; ++c) z[c] = x[0][c];
+    z[P - 1] = x[0][0];
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < P; ++a) {
+#pragma unroll
+      for (int b = a; b < P; ++b) {
+        acc[t] = fma(z[a] * om, z[b], acc[t]);
+        ++t;
+      }
+    }
+  }
+  __shared__ double sh[TL_T / 32][NT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const double v = warp_sum(acc[t]);
+    if (lane == 0) sh[warp][t] = v;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NT; t += TL_T) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < TL_T / 32; ++q) v += sh[q][t];
+    partials[(size_t)blockIdx.x * NT + t] = v;
+  }
+}
+
+template <int NC, bool WEIGHTED>
+static void launch_tail_gram(lfe_ctx* h, const TailCols& cols, const TailTabs& T, const double* w, int64_t n, int ldc,
+                             size_t smem, bool vec, double* gram_out, cudaStream_t s) {
+  constexpr int R = TailCfg<NC>::R;
+  constexpr int P = NC + 1, NT = P * (P + 1) / 2;
+  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)TL_T * R), NC <= 8 ? 2 : 1);
+  DevBuf<double> partials((size_t)blocks * NT, s);
+  // staged tables (<= 48 KB dynamic) + the static reduction scratch can exceed the 48 KB default carve-out
+  if (vec && R > 1) {
+    if (smem > 32 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(k_tail_gram<NC, R, true, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tail_gram<NC, R, true, WEIGHTED><<<blocks, TL_T, smem, s>>>(cols, T, w, n, ldc, partials);
+  } else {
+    if (smem > 32 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(k_tail_gram<NC, 1, false, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tail_gram<NC, 1, false, WEIGHTED><<<blocks, TL_T, smem, s>>>(cols, T, w, n, ldc, partials);
+  }
+  KERNEL_CHECK();
+  k_gram_final<<<1, 256, 0, s>>>(partials, blocks, P, gram_out);
+  KERNEL_CHECK();
+  h->n_launches += 2;
+}
+
+// gram_out (P x P, P = C + 1, order [1, x_1..x_k, y]) = Z' diag(w) Z of the demeaned columns; cols[0] = y (raw)
+void gram_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* weights, const TailTabs& T,
+                     int ldc, size_t smem, double* gram_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 9);
+  LFE_REQUIRE(C >= 1 && C <= TL_MAXC, "gram_fused: C=%d out of range", C);
+  const int P = C + 1;
+  if (n <= 0) {
+    CUDA_CHECK(cudaMemsetAsync(gram_out, 0, (size_t)P * P * sizeof(double), s));
+  } else {
+    TailCols tc;
+    for (int c = 0; c < C; ++c) tc.col[c] = cols[c];
+    const bool vec = tail_aligned(tc, C, T, weights);
+#define TG_CASE(NC_)                                                                                     \
+  case NC_:                                                                                              \
+    if (weights) launch_tail_gram<NC_, true>(h, tc, T, weights, n, ldc, smem, vec, gram_out, s);         \
+    else launch_tail_gram<NC_, false>(h, tc, T, nullptr, n, ldc, smem, vec, gram_out, s);                \
+    break;
+    switch (C) {
+      TG_CASE(1) TG_CASE(2) TG_CASE(3) TG_CASE(4) TG_CASE(5) TG_CASE(6) TG_CASE(7) TG_CASE(8) TG_CASE(9) TG_CASE(10)
+      TG_CASE(11)
+    }
+#undef TG_CASE
+  }
+  if (h->world > 1) comm_allreduce(h, gram_out, (int64_t)P * P, 0, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,21 +49,21 @@ __device__ __forceinline__ void load4_i32(const int32_t* __restrict__ p, int64_t
 
 // Fold PJ_I consecutive entries into the thread's open run (cur, run): equal keys accumulate, a key change
 // flushes the finished run with RED.ADD.F64.  cur < 0 = no open run / padding entry.
-template <int NC>
-__device__ __forceinline__ void run_fold(int& cur, double run[NC], const int key[PJ_I], double v[PJ_I][NC],
+template <int NC, int I = PJ_I>
+__device__ __forceinline__ void run_fold(int& cur, double* run, const int* key, double (*v)[NC],
                                          double* __restrict__ acc, int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
   bool same = true;
 #pragma unroll
-  for (int e = 0; e < PJ_I; ++e) same = same && (key[e] == cur);
+  for (int e = 0; e < I; ++e) same = same && (key[e] == cur);
   if (same) {   // inside a long group of a sorted list no run ends here: straight-line adds
 #pragma unroll
-    for (int e = 0; e < PJ_I; ++e)
+    for (int e = 0; e < I; ++e)
 #pragma unroll
       for (int c = 0; c < NC; ++c) run[c] += v[e][c];
     return;
   }
 #pragma unroll
-  for (int e = 0; e < PJ_I; ++e) {
+  for (int e = 0; e < I; ++e) {
     if (key[e] == cur) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) run[c] += v[e][c];
@@ -108,15 +108,15 @@ __device__ __forceinline__ void warp_flush(int cur, double run[NC], double* __re
   }
 }
 
-// one batch of PJ_I entries per thread: fold + warp flush
-template <int NC>
-__device__ __forceinline__ void segmented_flush(const int key[PJ_I], double v[PJ_I][NC], double* __restrict__ acc,
+// one batch of I (default PJ_I) entries per thread: fold + warp flush
+template <int NC, int I = PJ_I>
+__device__ __forceinline__ void segmented_flush(const int* key, double (*v)[NC], double* __restrict__ acc,
                                                 int64_t ld_row, int acc_col0, int64_t ld_col = 1) {
   int cur = -1;
   double run[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) run[c] = 0.0;
-  run_fold<NC>(cur, run, key, v, acc, ld_row, acc_col0, ld_col);
+  run_fold<NC, I>(cur, run, key, v, acc, ld_row, acc_col0, ld_col);
   warp_flush<NC>(cur, run, acc, ld_row, acc_col0, ld_col);
 }
 
@@ -160,11 +160,12 @@ __device__ __forceinline__ void bulk_add_drain() { asm volatile("cp.async.bulk.w
 
 // true when no two neighbouring rows of the warp (thread-internal or across lanes) share a key: every row is its
 // own run and can go out as one bulk reduce; otherwise the caller takes the run-merging RED path
-__device__ __forceinline__ bool warp_keys_all_distinct_neighbours(const int key[PJ_I]) {
+template <int I = PJ_I>
+__device__ __forceinline__ bool warp_keys_all_distinct_neighbours(const int* key) {
   bool dup = false;
 #pragma unroll
-  for (int e = 0; e + 1 < PJ_I; ++e) dup = dup || (key[e] == key[e + 1] && key[e] >= 0);
-  const int prev_last = __shfl_up_sync(0xffffffffu, key[PJ_I - 1], 1);
+  for (int e = 0; e + 1 < I; ++e) dup = dup || (key[e] == key[e + 1] && key[e] >= 0);
+  const int prev_last = __shfl_up_sync(0xffffffffu, key[I - 1], 1);
   dup = dup || ((threadIdx.x & 31) > 0 && prev_last == key[0] && key[0] >= 0);
   return !__any_sync(0xffffffffu, dup);
 }

@@ -7,6 +7,7 @@
 // row-major G x k table (one or two 32-byte sectors per row) whose Gram is the meat.  The k x k sandwich algebra runs in one CTA.
 #include "common.cuh"
 #include "segreduce.cuh"
+#include "tail.cuh"
 
 void gram_core(lfe_ctx* h, const double* const* cols, int C, int64_t n, const double* w, const double* r,
                int add_intercept, double* gram_out, cudaStream_t s, int64_t stride = 1);
@@ -401,6 +402,261 @@ static void fused_oneway_cluster(lfe_ctx* h, const double* const* cols, int k, i
   k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
   KERNEL_CHECK();
   h->n_launches += 7;
+}
+
+// ---- the same pass fed from (raw columns, FE tables) ---------------------------------------------------
+// x~ / y~ are formed in registers (tail.cuh), so lfe_demean_plan_fit never writes the demeaned columns.
+// MODE 0: IID (rss / tss moments only); 1: HC1 (meat triangle of x~ with omega = w r^2); 2: one-way cluster scores.
+template <int NC, int R, bool VEC, int MODE>
+__global__ void __launch_bounds__(TL_T) k_tail_resid(TailCols cols, TailTabs T, const double* __restrict__ beta_full,
+                                                     const double* __restrict__ w, const int32_t* __restrict__ key,
+                                                     int64_t n, int ldc, double* __restrict__ S, int ldS,
+                                                     uint32_t* __restrict__ present, double* __restrict__ partials,
+                                                     double* __restrict__ meat_partials, bool bulk) {
+  constexpr int K = NC - 1;                       // regressors
+  constexpr int KS = K > 0 ? K : 1;
+  constexpr int NTM = KS * (KS + 1) / 2;
+  extern __shared__ __align__(16) double tl_smem[];
+  const double* tabs[LFE_MAX_FE];
+  // dynamic shared memory: [bulk-reduce staging slots of all threads][staged tables]
+  const int slot_doubles = (MODE == 2 && bulk) ? TL_T * BulkRow<KS>::SLOT_DOUBLES : 0;
+  double* my_slots = tl_smem + (size_t)threadIdx.x * BulkRow<KS>::SLOT_DOUBLES;
+  stage_tables(T, ldc, tl_smem + slot_doubles, tabs);
+  int slot = 0;
+  __shared__ double sb[NC];
+  if (threadIdx.x < NC) sb[threadIdx.x] = beta_full[threadIdx.x];
+  __syncthreads();
+  const bool vec2 = (ldc & 1) == 0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  double macc[MODE == 1 ? NTM : 1];
+#pragma unroll
+  for (int t = 0; t < (MODE == 1 ? NTM : 1); ++t) macc[t] = 0.0;
+  // chunk loop: uniform per CTA, so the warp collectives of the score flush see all 32 lanes
+  const int64_t nchunk = ceil_div64(n, (int64_t)TL_T * R);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t base = (ch * TL_T + threadIdx.x) * R;
+    double x[R][NC];
+    bool valid[R];
+    double v[R][KS];
+    int kk[R];
+    if (VEC && base + R <= n) {
+      tail_rows<NC, R, true>(cols, T, tabs, ldc, vec2, base, n, x, valid);
+    } else {
+      tail_rows<NC, R, false>(cols, T, tabs, ldc, vec2, base, n, x, valid);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double res = x[r][0] - sb[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c) res = fma(-sb[c], x[r][c], res);
+      if (!valid[r]) res = 0.0;
+      const double we = (w && valid[r]) ? __ldcs(w + base + r) : 1.0;
+      const double r2 = res * res;
+      a0 += r2;
+      a1 += we * r2;
+      const double d = valid[r] ? x[r][0] : 0.0;
+      a2 += d;
+      a3 = fma(d, d, a3);
+      if (MODE == 1) {
+        const double om = we * r2;
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          const double za = x[r][1 + a] * om;
+#pragma unroll
+          for (int b = a; b < K; ++b) {
+            macc[t] = fma(za, x[r][1 + b], macc[t]);
+            ++t;
+          }
+        }
+      }
+      if (MODE == 2) {
+        const double rw = res * we;
+#pragma unroll
+        for (int c = 0; c < K; ++c) v[r][c] = x[r][1 + c] * rw;
+        kk[r] = valid[r] ? __ldcs(key + base + r) : -1;
+        if (valid[r]) present[kk[r]] = 1u;
+      }
+    }
+    if (MODE == 2) {
+      if (bulk && warp_keys_all_distinct_neighbours<R>(kk)) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (kk[r] >= 0) bulk_add_row<KS>(S + (size_t)kk[r] * ldS, v[r], my_slots, slot);
+      } else {
+        segmented_flush<KS, R>(kk, v, S, ldS, 0, 1);
+      }
+    }
+  }
+  if (MODE == 2 && bulk) bulk_add_drain();
+  __shared__ double sh[TL_T / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if (lane == 0) { sh[warp][0] = a0; sh[warp][1] = a1; sh[warp][2] = a2; sh[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int q = 0; q < TL_T / 32; ++q) t += sh[q][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+  }
+  if (MODE == 1) {
+    __shared__ double shm[TL_T / 32][NTM];
+#pragma unroll
+    for (int t = 0; t < NTM; ++t) {
+      const double q = warp_sum(macc[t]);
+      if (lane == 0) shm[warp][t] = q;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NTM; t += TL_T) {
+      double q = 0.0;
+#pragma unroll
+      for (int u = 0; u < TL_T / 32; ++u) q += shm[u][t];
+      meat_partials[(size_t)blockIdx.x * NTM + t] = q;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_meat_final(const double* __restrict__ partials, int nblocks, int K,
+                                                    double* __restrict__ out) {
+  const int NT = K * (K + 1) / 2;
+  for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * NT + t];
+    int a = 0, rem = t;
+    while (rem >= K - a) { rem -= K - a; ++a; }
+    const int bb = a + rem;
+    out[a * K + bb] = s;
+    out[bb * K + a] = s;
+  }
+}
+
+template <int NC, int MODE>
+static void launch_tail_resid(lfe_ctx* h, const TailCols& tc, const TailTabs& T, const double* beta_full, const double* w,
+                              const int32_t* key, int64_t n, int ldc, size_t tab_smem, bool vec, double* S, int ldS,
+                              uint32_t* present, double* partials, double* meat_partials, bool bulk, int blocks,
+                              cudaStream_t s) {
+  constexpr int R = TailCfg<NC>::R;
+  constexpr int KS = NC - 1 > 0 ? NC - 1 : 1;
+  const size_t smem = tab_smem + ((MODE == 2 && bulk) ? (size_t)TL_T * BulkRow<KS>::SLOT_DOUBLES * sizeof(double) : 0);
+  if (vec && R > 1) {
+    if (smem > 32 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(k_tail_resid<NC, R, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tail_resid<NC, R, true, MODE><<<blocks, TL_T, smem, s>>>(tc, T, beta_full, w, key, n, ldc, S, ldS, present, partials,
+                                                               meat_partials, bulk);
+  } else {
+    if (smem > 32 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(k_tail_resid<NC, 1, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tail_resid<NC, 1, false, MODE><<<blocks, TL_T, smem, s>>>(tc, T, beta_full, w, key, n, ldc, S, ldS, present, partials,
+                                                                meat_partials, bulk);
+  }
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
+// residual statistics + IID / HC1 / one-way clustered SEs of the fit whose demeaned columns are (cols, T): the
+// counterpart of resid_vcov_impl without materialised x~.  cols[0] = y (raw), C = k + 1 <= TL_MAXC.
+void resid_vcov_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const TailTabs& T, int ldc,
+                           size_t tab_smem, const double* beta_full, const double* Binv, int vcov_kind, const int32_t* cl,
+                           int64_t Gcap, const double* weights, int ssc, int64_t n_obs, int64_t df_resid, double* se_out,
+                           double* vcov_out, double* stats_out, int64_t* n_clusters_out, cudaStream_t s) {
+  PhaseTimer t(h, s, 11);
+  const bool cl_local = (vcov_kind & LFE_VCOV_CLUSTER_LOCAL) != 0;
+  vcov_kind &= ~LFE_VCOV_CLUSTER_LOCAL;
+  const int k = C - 1;
+  LFE_REQUIRE(C >= 1 && C <= TL_MAXC, "resid_vcov_fused: C=%d out of range", C);
+  TailCols tc;
+  for (int c = 0; c < C; ++c) tc.col[c] = cols[c];
+  const bool vec = tail_aligned(tc, C, T, weights) && (vcov_kind != LFE_VCOV_CLUSTER || ((((uintptr_t)cl) & 15) == 0));
+  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)TL_T * 2), C <= 8 ? 2 : 1);
+  const int ldS = (k >= 5 && (k & 1)) ? k + 1 : k;
+  const int ntm = k > 0 ? k * (k + 1) / 2 : 1;
+  DevBuf<double> partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
+  DevBuf<double> S, meat_partials;
+  DevBuf<uint32_t> present;
+  DevBuf<unsigned long long> tot(1, s);
+  tot.zero();
+  const bool bulk = vcov_kind == LFE_VCOV_CLUSTER && n >= 4096 && k >= 3 && (ldS & 1) == 0;
+  if (vcov_kind == LFE_VCOV_CLUSTER) {
+    S.alloc((size_t)Gcap * ldS, s); S.zero();
+    present.alloc(Gcap, s); present.zero();
+  }
+  if (vcov_kind == LFE_VCOV_HC1) meat_partials.alloc((size_t)blocks * ntm, s);
+  if (n > 0) {
+#define TR_CASE(NC_)                                                                                                   \
+  case NC_:                                                                                                            \
+    if (vcov_kind == LFE_VCOV_IID || k == 0)                                                                           \
+      launch_tail_resid<NC_, 0>(h, tc, T, beta_full, weights, cl, n, ldc, tab_smem, vec, S, ldS, present, partials,    \
+                                meat_partials, false, blocks, s);                                                      \
+    else if (vcov_kind == LFE_VCOV_HC1)                                                                                \
+      launch_tail_resid<NC_, 1>(h, tc, T, beta_full, weights, cl, n, ldc, tab_smem, vec, S, ldS, present, partials,    \
+                                meat_partials, false, blocks, s);                                                      \
+    else                                                                                                               \
+      launch_tail_resid<NC_, 2>(h, tc, T, beta_full, weights, cl, n, ldc, tab_smem, vec, S, ldS, present, partials,    \
+                                meat_partials, bulk, blocks, s);                                                       \
+    break;
+    switch (C) {
+      TR_CASE(1) TR_CASE(2) TR_CASE(3) TR_CASE(4) TR_CASE(5) TR_CASE(6) TR_CASE(7) TR_CASE(8) TR_CASE(9) TR_CASE(10)
+      TR_CASE(11)
+    }
+#undef TR_CASE
+    k_resid_final<<<1, 32, 0, s>>>(partials, blocks, (double)n, raw);
+    KERNEL_CHECK();
+  } else {
+    raw.zero();
+  }
+  if (h->world > 1) comm_allreduce(h, raw, 4, 0, s);
+  double* stats = stats_out ? stats_out : stats_local.p;
+  k_stats_from_raw<<<1, 32, 0, s>>>(raw, (double)n_obs, stats);
+  KERNEL_CHECK();
+  h->n_launches += 2;
+  if (k == 0) return;
+  DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
+  V.zero();
+  if (vcov_kind == LFE_VCOV_IID) {
+    CUDA_CHECK(cudaMemcpyAsync(V.p, Binv, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    k_scale_se<<<1, 256, 0, s>>>(V, k, 1.0, stats, 2, (double)df_resid, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+    return;
+  }
+  if (vcov_kind == LFE_VCOV_HC1) {
+    if (n > 0) {
+      k_meat_final<<<1, 256, 0, s>>>(meat_partials, blocks, k, meat);
+      KERNEL_CHECK();
+    } else {
+      meat.zero();
+    }
+    if (h->world > 1) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
+    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+    KERNEL_CHECK();
+    k_scale_se<<<1, 256, 0, s>>>(V, k, (double)n_obs / (double)df_resid, nullptr, 0, 1.0, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 3;
+    return;
+  }
+  // one-way cluster: number of clusters with at least one row, meat = S'S
+  if (h->world > 1 && !cl_local) comm_allreduce_int(h, present.p, Gcap, 0, 2, s);
+  k_sum_u32<<<launch_blocks(h, ceil_div64(Gcap, 1024), 8), 256, 0, s>>>(present, Gcap, tot);
+  KERNEL_CHECK();
+  if (h->world > 1 && cl_local) comm_allreduce_int(h, tot.p, 1, 1, 0, s);
+  unsigned long long ht = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&ht, tot.p, sizeof(ht), cudaMemcpyDeviceToHost, s));
+  if (h->world > 1 && !cl_local) comm_allreduce(h, S, Gcap * ldS, 0, s);
+  std::vector<const double*> sc(k);
+  for (int c = 0; c < k; ++c) sc[c] = S.p + c;
+  gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, ldS);
+  if (h->world > 1 && cl_local) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
+  k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
+  KERNEL_CHECK();
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  const int64_t G = (int64_t)ht;
+  if (n_clusters_out) n_clusters_out[0] = G;
+  LFE_REQUIRE(G > 1, "clustered vcov: a single cluster (division by zero in G/(G-1))");
+  double adj = (double)G / (double)(G - 1);
+  if (ssc) adj *= (double)(n_obs - 1) / (double)df_resid;
+  k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
+  KERNEL_CHECK();
+  h->n_launches += 4;
 }
 
 void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, const double* beta_full,

@@ -464,6 +464,34 @@ class DemeanPlan:
                                                eng.stream))
         return int(it.value), float(mm.value), bool(cv.value)
 
+    FIT_MAX_COLS = 11    # TL_MAXC of csrc/tail.cuh: y + regressors handled by lfe_demean_plan_fit
+
+    def fit(self, cols: list[torch.Tensor], fe_order: list[int], tol: float, max_iter: int, min_iter: int,
+            vcov_kind: int, cl_codes: torch.Tensor | None, n_cl_groups: int, ssc: bool, n_obs: int, df_resid: int):
+        """lfe_demean_plan_fit: sweeps + normal equations + solve + residual statistics + IID / HC1 / one-way
+        clustered SEs without materialising the demeaned columns (``cols`` are only read; cols[0] = y).
+        -> dict(beta_full, se, vcov, stats, iterations, max_mean, converged, n_clusters)"""
+        eng = self.eng
+        eng._check_dev(*cols, cl_codes)
+        k = len(cols) - 1
+        for t in cols:
+            if t.dtype != torch.float64 or t.numel() != self.n:
+                raise ValueError("fit columns must be float64 with one value per plan row")
+        if cl_codes is not None and (cl_codes.dtype != torch.int32 or cl_codes.numel() != self.n):
+            raise ValueError("cluster codes must be int32 with one value per plan row")
+        out = eng.empty((k + 1) + max(k, 1) + max(k * k, 1) + 4, torch.float64)
+        beta, se = out[: k + 1], out[k + 1: k + 1 + max(k, 1)]
+        V = out[k + 1 + max(k, 1): k + 1 + max(k, 1) + max(k * k, 1)]
+        stats = out[-4:]
+        it, mm, cv, ncl = C.c_int(0), C.c_double(0.0), C.c_int(0), C.c_int64(0)
+        capi.check(eng.lib.lfe_demean_plan_fit(
+            eng.h, self.p, capi.ptr_array([t.data_ptr() for t in cols]), len(cols), capi.i32_array(fe_order), float(tol),
+            int(max_iter), int(min_iter), 0, int(vcov_kind), eng._p(cl_codes), int(n_cl_groups), 1 if ssc else 0,
+            int(n_obs), int(df_resid), eng._p(beta), eng._p(se), eng._p(V), eng._p(stats), C.byref(it), C.byref(mm),
+            C.byref(cv), C.byref(ncl), eng.stream))
+        return dict(beta_full=beta, se=se[:k], vcov=V[: k * k].view(k, k), stats=stats, packed=out,
+                    iterations=int(it.value), max_mean=float(mm.value), converged=bool(cv.value), n_clusters=int(ncl.value))
+
     def close(self):
         if getattr(self, "p", None):
             self.eng.lib.lfe_demean_plan_destroy(self.eng.h, self.p)

@@ -610,3 +610,69 @@ def test_demean_plan_out_of_place_matches_in_place(eng):
     for x, y_, s0, k0 in zip(a, b, src, keep):
         assert torch.equal(s0, k0)
         assert float((x - y_).abs().max()) < 1e-12        # fp64 atomics: summation order differs run to run
+
+
+# ------------------------------------------------------------------------------------------------
+# lfe_demean_plan_fit: the fused tail (x~ formed in registers) equals the materialised chain
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,Gs,weighted,n,offset", [
+    (6, (5000, 60), False, 200_003, 0),      # rows-per-thread 4, n % 4 != 0
+    (6, (5000, 60), True, 200_000, 0),
+    (3, (3000, 700, 12), False, 150_001, 0),  # odd narrow tables (no 128-bit gathers), three FEs
+    (8, (4000, 30), False, 120_002, 0),      # rows-per-thread 2
+    (11, (4000, 500), True, 90_001, 0),      # rows-per-thread 1, padded table rows (ld 12)
+    (1, (300, 7), False, 10_007, 0),         # no regressors
+    (5, (2000, 40), False, 50_003, 1),       # unaligned column views -> scalar path
+    (4, (800,), False, 30_000, 0),           # single FE (within transform)
+])
+def test_plan_fit_matches_run_gram_solve_vcov(eng, C, Gs, weighted, n, offset):
+    rng = np.random.default_rng(C * 1000 + len(Gs))
+    k = C - 1
+    fe = [rng.integers(0, g, n).astype(np.int32) for g in Gs]
+    X = rng.normal(size=(n, k)) + 0.3 * rng.normal(size=Gs[0])[fe[0]][:, None]
+    y = X @ (1 + 0.1 * np.arange(k)) + rng.normal(size=Gs[0])[fe[0]] + rng.normal(size=n) * (1 + 0.3 * (fe[-1] % 3))
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    cl = rng.integers(0, 400, n).astype(np.int32)
+
+    def col(a):
+        if not offset:
+            return dev(a)
+        buf = torch.empty(n + offset, dtype=torch.float64, device="cuda")
+        buf[offset:] = torch.from_numpy(a).cuda()
+        return buf[offset:]
+
+    raw = [col(y)] + [col(np.ascontiguousarray(X[:, j])) for j in range(k)]
+    codes = [dev(f) for f in fe]
+    dw = dev(w) if weighted else None
+    order = sorted(range(len(Gs)), key=lambda j: Gs[j])
+    F = len(Gs)
+    mi, mn = (1, 2) if F == 1 else (50, 3)
+    plan = eng.demean_plan(codes, list(Gs), dw)
+    # the materialised chain
+    dm = [torch.empty_like(t) for t in raw]
+    it_ref = plan.run(dm, order, 1e-8, mi, mn, src=raw)
+    gram = eng.gram(dm[1:] + [dm[0]], dw, add_intercept=True)
+    p = k + 1
+    beta_full, Ainv, _ = eng.solve_spd(gram[:p, :p].contiguous(), gram[:p, p].contiguous())
+    df = n - p - (sum(Gs) - F)
+    for kind, clc, G in ((0, None, 0), (1, None, 0), (2, dev(cl), 400)):
+        out = plan.fit(raw, order, 1e-8, mi, mn, kind, clc, G, True, n, df)
+        assert out["iterations"] == it_ref[0] and out["converged"] == it_ref[2]
+        np.testing.assert_allclose(out["beta_full"].cpu().numpy()[1:], beta_full.cpu().numpy()[1:], rtol=1e-10, atol=1e-14)
+        st = out["stats"].cpu().numpy()
+        if k:
+            B = Ainv[1:, 1:].contiguous()
+            ref = eng.resid_vcov(dm, beta_full, B, kind, [clc] if clc is not None else None, [G] if G else None, dw,
+                                 True, n, df)
+            np.testing.assert_allclose(out["se"].cpu().numpy(), ref["se"].cpu().numpy(), rtol=1e-9)
+            np.testing.assert_allclose(out["vcov"].cpu().numpy(), ref["vcov"].cpu().numpy(), rtol=1e-8, atol=1e-20)
+            rst = ref["stats"].cpu().numpy()
+            assert st[0] == pytest.approx(rst[0], rel=1e-11) and st[1] == pytest.approx(rst[1], rel=1e-9)
+            if kind == 2:
+                assert out["n_clusters"] == ref["n_clusters"][0] == len(np.unique(cl))
+        else:
+            r = (dm[0] - beta_full[0]).cpu().numpy()
+            assert st[0] == pytest.approx(float((r ** 2).sum()), rel=1e-11)
+    # the raw columns were only read
+    np.testing.assert_array_equal(raw[0].cpu().numpy(), y)
+    plan.close()
