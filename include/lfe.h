@@ -281,6 +281,23 @@ int lfe_shard_plan(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_grou
 int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_counts /*[host]*/,
                        const int64_t* recv_counts /*[host]*/, const void* const* cols_in, const int* dtypes,
                        const int64_t* i32_sub /*[host], nullable*/, int K, int64_t n, void* const* cols_out, void* stream);
+/* ---- host ingest: pageable memory -> device -------------------------------------------------
+ * The reference's API receives DataFrames / NumPy columns (polars_impl.py:342-347): pageable host memory, which a
+ * plain cudaMemcpyAsync stages synchronously on one driver thread.  The uploader owns a ring of `n_slots` pinned
+ * chunks of `chunk_bytes`; `n_threads` host threads memcpy the pieces of a chunk into its slot and each chunk leaves
+ * with one cudaMemcpyAsync on `copy_stream`.  enqueue returns at once (host_src must stay valid and unchanged until
+ * the job's copy completed: lfe_uploader_stream_wait + stream completion, or lfe_uploader_drain); columns are
+ * transferred in enqueue order.  lfe_uploader_stream_wait blocks the calling HOST thread until the job's last chunk
+ * has been issued and then makes `compute_stream` wait for it on the device.  lfe_uploader_drain waits for every
+ * job and forgets the tickets.                                                                          */
+typedef struct lfe_uploader* lfe_uploader_t;
+int lfe_uploader_create(lfe_handle h, int64_t chunk_bytes, int n_slots, int n_threads, lfe_uploader_t* out);
+int lfe_uploader_destroy(lfe_uploader_t u);
+int lfe_uploader_enqueue(lfe_uploader_t u, const void* host_src /*[host]*/, int64_t nbytes, void* dev_dst,
+                         void* copy_stream, int64_t* ticket_out /*[host]*/);
+int lfe_uploader_stream_wait(lfe_uploader_t u, int64_t ticket, void* compute_stream);
+int lfe_uploader_drain(lfe_uploader_t u);
+
 /* sum all-reduce of a device double buffer over the attached communicator (no-op if none) */
 int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream);
 

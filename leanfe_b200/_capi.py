@@ -29,6 +29,7 @@ EXPORTS = [
     "lfe_demean_plan_destroy", "lfe_demean_plan_fit", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
     "lfe_allreduce_f64", "lfe_shard_plan", "lfe_shard_exchange",
+    "lfe_uploader_create", "lfe_uploader_destroy", "lfe_uploader_enqueue", "lfe_uploader_stream_wait", "lfe_uploader_drain",
 ]
 
 
@@ -89,6 +90,11 @@ def load_library() -> C.CDLL:
     lib.lfe_comm_set_active.argtypes = [vp, i32]
     lib.lfe_compress_merge.argtypes = [vp, P(vp), P(i64), i32, vp, vp, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
     lib.lfe_allreduce_f64.argtypes = [vp, vp, i64, vp]
+    lib.lfe_uploader_create.argtypes = [vp, i64, i32, i32, P(vp)]
+    lib.lfe_uploader_destroy.argtypes = [vp]
+    lib.lfe_uploader_enqueue.argtypes = [vp, vp, i64, vp, vp, P(i64)]
+    lib.lfe_uploader_stream_wait.argtypes = [vp, i64, vp]
+    lib.lfe_uploader_drain.argtypes = [vp]
     lib.lfe_shard_plan.argtypes = [vp, vp, i64, i64, P(i64), P(i64), P(i64), vp, vp]
     lib.lfe_shard_exchange.argtypes = [vp, vp, P(i64), P(i64), P(vp), P(i32), P(i64), i32, i64, P(vp), vp]
     for name in EXPORTS:

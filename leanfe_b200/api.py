@@ -130,193 +130,196 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     # every H2D copy is enqueued now, ids first: the id-only work below overlaps the fp64 uploads
     key_first = fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions] + [v for v, _ in factor_vars]
     up = Uploader(eng, frame, key_first + ([weights] if weights is not None else []) + needed)
-    numeric: dict[str, torch.Tensor] = {}
-    keys: dict[str, KeyColumn] = {}
+    try:
+        numeric: dict[str, torch.Tensor] = {}
+        keys: dict[str, KeyColumn] = {}
 
-    owned_ids: set[int] = set()      # device tensors created by this call (uploads, casts): safe to overwrite
+        owned_ids: set[int] = set()      # device tensors created by this call (uploads, casts): safe to overwrite
 
-    def num(name):
-        if name not in numeric:
-            src = up.get(name)
-            numeric[name] = to_device_f64(eng, src)
-            if name in up.events_seen or numeric[name] is not src:
-                owned_ids.add(id(numeric[name]))
-        return numeric[name]
+        def num(name):
+            if name not in numeric:
+                src = up.get(name)
+                numeric[name] = to_device_f64(eng, src)
+                if name in up.events_seen or numeric[name] is not src:
+                    owned_ids.add(id(numeric[name]))
+            return numeric[name]
 
-    def key(name, labels=False):
-        if name not in keys or (labels and keys[name].labels is None):
-            # multi-GPU: every key column except the shard key needs ONE code space shared by all ranks
-            keys[name] = to_device_key(eng, up.get(name), want_labels=labels, global_codes=dist and name != local_fe)
-        return keys[name]
+        def key(name, labels=False):
+            if name not in keys or (labels and keys[name].labels is None):
+                # multi-GPU: every key column except the shard key needs ONE code space shared by all ranks
+                keys[name] = to_device_key(eng, up.get(name), want_labels=labels, global_codes=dist and name != local_fe)
+            return keys[name]
 
-    fe_keys = [key(c) for c in fe_cols]
-    cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
-    base_x = list(x_cols)
-    extra_z = [z for z in instruments if z not in x_cols]
-    fe_card_order = [k_.n_groups for k_ in fe_keys]      # cardinalities that fix the sweep order (:485)
-    if dist and strategy != "compress":
-        if local_fe is None:
-            # library-side repartition: all key columns are coded in the shared code space; the rows
-            # move so that every group of the highest-cardinality FE lives on one rank
-            j_sh = max(range(len(fe_cols)), key=lambda j: fe_keys[j].n_groups)
-            local_fe = fe_cols[j_sh]
-            num_names = list(dict.fromkeys([y_col] + base_x + extra_z + ([weights] if weights is not None else [])
-                                           + [v for v, _, _ in interactions]))
-            key_names = list(dict.fromkeys(fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions]
-                                           + [v for v, _ in factor_vars]))
-            for nm in [f for _, f, _ in interactions] + [v for v, _ in factor_vars]:
-                key(nm, labels=True)
-            tensors = [num(nm) for nm in num_names] + [key(nm).codes for nm in key_names]
-            sp = eng.shard_plan(fe_keys[j_sh].codes, fe_keys[j_sh].n_groups)
-            lo, hi = sp["cuts"][eng.rank], sp["cuts"][eng.rank + 1]
-            moved = eng.shard_exchange(sp, tensors, [0] * len(num_names) + [lo if nm == local_fe else 0 for nm in key_names])
-            del tensors
-            for nm, t in zip(num_names, moved):
-                numeric[nm] = t
-                owned_ids.add(id(t))
-            for nm, t in zip(key_names, moved[len(num_names):]):
-                keys[nm] = KeyColumn(t, (hi - lo) if nm == local_fe else keys[nm].n_groups, keys[nm].labels, None)
-            fe_keys = [keys[c] for c in fe_cols]
-            cl_keys = [keys[c] for c in cluster_cols] if cluster_cols else []
-        else:
-            # caller-partitioned rows: the shard key was coded rank-locally; its global cardinality (for the sweep
-            # order, which must be the same on every rank) is the sum over ranks
-            j_sh = fe_cols.index(local_fe)
-            fe_card_order[j_sh] = int(eng.allreduce(torch.tensor([float(fe_keys[j_sh].n_groups)], dtype=torch.float64,
-                                                                 device=eng.device)).item())
-
-    def xsrc(name, keep_int):
-        # YOCO only groups by the regressors: integer-typed columns (dummies, counts) are factorised as they are,
-        # without a 8-byte-per-row fp64 copy
-        t = up.get(name)
-        if keep_int and isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.uint8, torch.int32, torch.int64):
-            return t
-        return num(name)
-
-    iv_state = {"k": None, "z_idx": []}
-
-    def columns(keep_int=False):
-        """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
-        y_ = num(y_col)
-        X_ = [xsrc(c, keep_int) for c in base_x]
-        names = list(base_x)
-        w_ = num(weights) if weights is not None else None
-        # interactions then factors (polars_impl.py:350-365); labels come from the original values
-        for var, factor, ref in interactions:
-            kc = key(factor, labels=True)
-            ref_cat = resolve_reference(kc.labels, ref, factor)
-            base = num(var)
-            for j, cat in enumerate(kc.labels):
-                if cat != ref_cat:
-                    X_.append(base * (kc.codes == j))
-                    names.append(f"{var}_{cat}")
-        for var, ref in factor_vars:
-            kc = key(var, labels=True)
-            ref_cat = resolve_reference(kc.labels, ref, var)
-            for j, cat in enumerate(kc.labels):
-                if cat != ref_cat:
-                    X_.append((kc.codes == j).to(torch.uint8 if keep_int else torch.float64))
-                    names.append(f"{var}_{cat}")
-        # instruments ride along as extra columns: they are demeaned with y and X (polars_impl.py:431, 486); an
-        # exogenous regressor listed among the instruments is the same column, demeaned once
-        iv_state["k"] = len(names)
-        for z in instruments:
-            if z not in names:
-                X_.append(num(z))
-                names.append(z)
-        iv_state["z_idx"] = [names.index(z) for z in instruments]
-        return y_, X_, names, w_
-
-    cols_cache = []
-
-    def get_columns():
-        if not cols_cache:
-            cols_cache.append(columns())
-            owned_ids.update(id(t) for t in cols_cache[0][1][len(base_x):])      # expanded dummies are ours
-        return cols_cache[0]
-
-    get_columns.owned = lambda t: id(t) in owned_ids
-    if not interactions and not factor_vars and weights is None:
-        # plain columns: they can be handed out one by one, as each upload completes
-        get_columns.lazy = dict(y=y_col, x=base_x + extra_z, get=num,
-                                pending=lambda: any(nm in up.events for nm in [y_col] + base_x + extra_z))
-        iv_state.update(k=len(base_x), z_idx=[(base_x + extra_z).index(z) for z in instruments])
-
-    n0 = fe_keys[0].codes.numel() if fe_keys else get_columns()[0].numel()
-
-    if sample_frac is not None:
-        # the reference samples with Polars' RNG (seed 42, polars_impl.py:359-360); not reproducible without
-        # Polars, so sampled fits are parity-unpinned (SURVEY A.6.9)
-        g = torch.Generator(device=eng.device)
-        g.manual_seed(42)
-        m = int(n0 * sample_frac)
-        idx = torch.randperm(n0, generator=g, device=eng.device)[:m].sort().values
-        y, X, names, w = get_columns()
-        cols_cache[0] = (y[idx].contiguous(), [c[idx].contiguous() for c in X], names,
-                         w[idx].contiguous() if w is not None else None)
-        # cardinalities, group sizes and the strategy rule see the SAMPLED frame, as in the reference
-        # (polars_impl.py:359-373: sample first, n_unique afterwards): re-rank the sampled codes so that levels
-        # without a sampled row do not count towards fe_dims / df_resid
-        def resample(k_):
-            c_, G_, _ = eng.factorize(k_.codes[idx].contiguous())
-            return KeyColumn(c_, G_, None, eng.factorize_counts(c_, G_))
-
-        by_id = {id(k_): resample(k_) for k_ in {id(k_): k_ for k_ in fe_keys + cl_keys}.values()}
-        fe_keys = [by_id[id(k_)] for k_ in fe_keys]
-        cl_keys = [by_id[id(k_)] for k_ in cl_keys]
-        fe_card_order = [k_.n_groups for k_ in fe_keys]
-        n0 = m
-
-    fe_card = {c: k_.n_groups for c, k_ in zip(fe_cols, fe_keys)}
-    est_ratio = None
-    if strategy == "auto":
-        def ratio():
-            # distinct rows over set(x_cols + fe_cols) / N   (compress.py:232-253)
-            _, X, names, _ = get_columns()
-            names = names[: iv_state["k"]]
-            kcs = []
-            for nm in dict.fromkeys(names + fe_cols):
-                if nm in fe_cols:
-                    kcs.append(fe_keys[fe_cols.index(nm)])
-                else:
-                    c_, G_, _ = eng.factorize(X[names.index(nm)])
-                    kcs.append(KeyColumn(c_, G_))
-            if not kcs:
-                return 1.0
-            r = eng.compress([k_.codes for k_ in kcs], [k_.n_groups for k_ in kcs], None, count_only=True)
-            return r["n_compressed"] / max(n0, 1)
-
-        if not fe_cols:
-            est_ratio = ratio()
-            # (with instruments the reference would pick 'compress' here and silently drop them; we fit 2SLS)
-            strategy = "ols" if est_ratio >= 0.8 or instruments else "compress"
-        elif len(fe_cols) == 1:
-            strategy = "demean"
-        else:
-            # rules 1/2 of determine_strategy do not need the ratio; compute it only for the cost model
-            total, mx = sum(fe_card.values()), max(fe_card.values())
-            if mx > MAX_FE_LEVELS or total > 2 * MAX_FE_LEVELS:
-                strategy = "alt_proj"
+        fe_keys = [key(c) for c in fe_cols]
+        cl_keys = [key(c) for c in cluster_cols] if cluster_cols else []
+        base_x = list(x_cols)
+        extra_z = [z for z in instruments if z not in x_cols]
+        fe_card_order = [k_.n_groups for k_ in fe_keys]      # cardinalities that fix the sweep order (:485)
+        if dist and strategy != "compress":
+            if local_fe is None:
+                # library-side repartition: all key columns are coded in the shared code space; the rows
+                # move so that every group of the highest-cardinality FE lives on one rank
+                j_sh = max(range(len(fe_cols)), key=lambda j: fe_keys[j].n_groups)
+                local_fe = fe_cols[j_sh]
+                num_names = list(dict.fromkeys([y_col] + base_x + extra_z + ([weights] if weights is not None else [])
+                                               + [v for v, _, _ in interactions]))
+                key_names = list(dict.fromkeys(fe_cols + (cluster_cols or []) + [f for _, f, _ in interactions]
+                                               + [v for v, _ in factor_vars]))
+                for nm in [f for _, f, _ in interactions] + [v for v, _ in factor_vars]:
+                    key(nm, labels=True)
+                tensors = [num(nm) for nm in num_names] + [key(nm).codes for nm in key_names]
+                sp = eng.shard_plan(fe_keys[j_sh].codes, fe_keys[j_sh].n_groups)
+                lo, hi = sp["cuts"][eng.rank], sp["cuts"][eng.rank + 1]
+                moved = eng.shard_exchange(sp, tensors, [0] * len(num_names) + [lo if nm == local_fe else 0 for nm in key_names])
+                del tensors
+                for nm, t in zip(num_names, moved):
+                    numeric[nm] = t
+                    owned_ids.add(id(t))
+                for nm, t in zip(key_names, moved[len(num_names):]):
+                    keys[nm] = KeyColumn(t, (hi - lo) if nm == local_fe else keys[nm].n_groups, keys[nm].labels, None)
+                fe_keys = [keys[c] for c in fe_cols]
+                cl_keys = [keys[c] for c in cluster_cols] if cluster_cols else []
             else:
-                est_ratio = ratio()
-                strategy = determine_strategy(vcov, bool(instruments), fe_card, MAX_FE_LEVELS, n0,
-                                              iv_state["k"], est_ratio)
+                # caller-partitioned rows: the shard key was coded rank-locally; its global cardinality (for the sweep
+                # order, which must be the same on every rank) is the sum over ranks
+                j_sh = fe_cols.index(local_fe)
+                fe_card_order[j_sh] = int(eng.allreduce(torch.tensor([float(fe_keys[j_sh].n_groups)], dtype=torch.float64,
+                                                                     device=eng.device)).item())
 
-    if strategy == "compress":
-        y, X, x_cols, w = cols_cache[0] if cols_cache else columns(keep_int=True)
-        res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
-        res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
-    else:
-        lf = fe_cols.index(local_fe) if dist else -1
-        cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
-        w_early = num(weights) if weights is not None else None
-        res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
-                       max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None, fe_card_order)
-    if profile:
-        torch.cuda.synchronize(eng.device)
-        res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
-        eng.set_profiling(False)
-    return res
+        def xsrc(name, keep_int):
+            # YOCO only groups by the regressors: integer-typed columns (dummies, counts) are factorised as they are,
+            # without a 8-byte-per-row fp64 copy
+            t = up.get(name)
+            if keep_int and isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.uint8, torch.int32, torch.int64):
+                return t
+            return num(name)
+
+        iv_state = {"k": None, "z_idx": []}
+
+        def columns(keep_int=False):
+            """(y, X, names, w): the numeric columns, waited for / expanded only when first needed."""
+            y_ = num(y_col)
+            X_ = [xsrc(c, keep_int) for c in base_x]
+            names = list(base_x)
+            w_ = num(weights) if weights is not None else None
+            # interactions then factors (polars_impl.py:350-365); labels come from the original values
+            for var, factor, ref in interactions:
+                kc = key(factor, labels=True)
+                ref_cat = resolve_reference(kc.labels, ref, factor)
+                base = num(var)
+                for j, cat in enumerate(kc.labels):
+                    if cat != ref_cat:
+                        X_.append(base * (kc.codes == j))
+                        names.append(f"{var}_{cat}")
+            for var, ref in factor_vars:
+                kc = key(var, labels=True)
+                ref_cat = resolve_reference(kc.labels, ref, var)
+                for j, cat in enumerate(kc.labels):
+                    if cat != ref_cat:
+                        X_.append((kc.codes == j).to(torch.uint8 if keep_int else torch.float64))
+                        names.append(f"{var}_{cat}")
+            # instruments ride along as extra columns: they are demeaned with y and X (polars_impl.py:431, 486); an
+            # exogenous regressor listed among the instruments is the same column, demeaned once
+            iv_state["k"] = len(names)
+            for z in instruments:
+                if z not in names:
+                    X_.append(num(z))
+                    names.append(z)
+            iv_state["z_idx"] = [names.index(z) for z in instruments]
+            return y_, X_, names, w_
+
+        cols_cache = []
+
+        def get_columns():
+            if not cols_cache:
+                cols_cache.append(columns())
+                owned_ids.update(id(t) for t in cols_cache[0][1][len(base_x):])      # expanded dummies are ours
+            return cols_cache[0]
+
+        get_columns.owned = lambda t: id(t) in owned_ids
+        if not interactions and not factor_vars and weights is None:
+            # plain columns: they can be handed out one by one, as each upload completes
+            get_columns.lazy = dict(y=y_col, x=base_x + extra_z, get=num,
+                                    pending=lambda: any(nm in up.events for nm in [y_col] + base_x + extra_z))
+            iv_state.update(k=len(base_x), z_idx=[(base_x + extra_z).index(z) for z in instruments])
+
+        n0 = fe_keys[0].codes.numel() if fe_keys else get_columns()[0].numel()
+
+        if sample_frac is not None:
+            # the reference samples with Polars' RNG (seed 42, polars_impl.py:359-360); not reproducible without
+            # Polars, so sampled fits are parity-unpinned (SURVEY A.6.9)
+            g = torch.Generator(device=eng.device)
+            g.manual_seed(42)
+            m = int(n0 * sample_frac)
+            idx = torch.randperm(n0, generator=g, device=eng.device)[:m].sort().values
+            y, X, names, w = get_columns()
+            cols_cache[0] = (y[idx].contiguous(), [c[idx].contiguous() for c in X], names,
+                             w[idx].contiguous() if w is not None else None)
+            # cardinalities, group sizes and the strategy rule see the SAMPLED frame, as in the reference
+            # (polars_impl.py:359-373: sample first, n_unique afterwards): re-rank the sampled codes so that levels
+            # without a sampled row do not count towards fe_dims / df_resid
+            def resample(k_):
+                c_, G_, _ = eng.factorize(k_.codes[idx].contiguous())
+                return KeyColumn(c_, G_, None, eng.factorize_counts(c_, G_))
+
+            by_id = {id(k_): resample(k_) for k_ in {id(k_): k_ for k_ in fe_keys + cl_keys}.values()}
+            fe_keys = [by_id[id(k_)] for k_ in fe_keys]
+            cl_keys = [by_id[id(k_)] for k_ in cl_keys]
+            fe_card_order = [k_.n_groups for k_ in fe_keys]
+            n0 = m
+
+        fe_card = {c: k_.n_groups for c, k_ in zip(fe_cols, fe_keys)}
+        est_ratio = None
+        if strategy == "auto":
+            def ratio():
+                # distinct rows over set(x_cols + fe_cols) / N   (compress.py:232-253)
+                _, X, names, _ = get_columns()
+                names = names[: iv_state["k"]]
+                kcs = []
+                for nm in dict.fromkeys(names + fe_cols):
+                    if nm in fe_cols:
+                        kcs.append(fe_keys[fe_cols.index(nm)])
+                    else:
+                        c_, G_, _ = eng.factorize(X[names.index(nm)])
+                        kcs.append(KeyColumn(c_, G_))
+                if not kcs:
+                    return 1.0
+                r = eng.compress([k_.codes for k_ in kcs], [k_.n_groups for k_ in kcs], None, count_only=True)
+                return r["n_compressed"] / max(n0, 1)
+
+            if not fe_cols:
+                est_ratio = ratio()
+                # (with instruments the reference would pick 'compress' here and silently drop them; we fit 2SLS)
+                strategy = "ols" if est_ratio >= 0.8 or instruments else "compress"
+            elif len(fe_cols) == 1:
+                strategy = "demean"
+            else:
+                # rules 1/2 of determine_strategy do not need the ratio; compute it only for the cost model
+                total, mx = sum(fe_card.values()), max(fe_card.values())
+                if mx > MAX_FE_LEVELS or total > 2 * MAX_FE_LEVELS:
+                    strategy = "alt_proj"
+                else:
+                    est_ratio = ratio()
+                    strategy = determine_strategy(vcov, bool(instruments), fe_card, MAX_FE_LEVELS, n0,
+                                                  iv_state["k"], est_ratio)
+
+        if strategy == "compress":
+            y, X, x_cols, w = cols_cache[0] if cols_cache else columns(keep_int=True)
+            res = _fit_compress(eng, y, X, x_cols, fe_keys, fe_cols, cl_keys, cluster_cols, w, vcov, vkind, ssc, n0)
+            res.formula, res.fe_cols, res.compression_ratio = formula, fe_cols, est_ratio
+        else:
+            lf = fe_cols.index(local_fe) if dist else -1
+            cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
+            w_early = num(weights) if weights is not None else None
+            res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
+                           max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None, fe_card_order)
+        if profile:
+            torch.cuda.synchronize(eng.device)
+            res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
+            eng.set_profiling(False)
+        return res
+    finally:
+        up.close()      # every staged host->device copy has completed before the caller's arrays may go away
 
 
 # ------------------------------------------------------------------------------------------------

@@ -195,6 +195,13 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
                          const void* const* cols_in, const int* dtypes, const int64_t* i32_sub, int K, int64_t n,
                          void* const* cols_out, cudaStream_t s);
 
+struct lfe_uploader;
+lfe_uploader* uploader_create(lfe_ctx* h, int64_t chunk_bytes, int n_slots, int n_threads);
+void uploader_destroy(lfe_uploader* u);
+void uploader_drain(lfe_uploader* u);
+int64_t uploader_enqueue(lfe_uploader* u, const void* host_src, int64_t nbytes, void* dev_dst, cudaStream_t copy_stream);
+void uploader_stream_wait(lfe_uploader* u, int64_t ticket, cudaStream_t compute_stream);
+
 // ---- exported functions -------------------------------------------------------------------------------
 extern "C" {
 
@@ -524,6 +531,37 @@ int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_c
               "lfe_shard_exchange: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
   shard_exchange_impl(h, order, send_counts, recv_counts, cols_in, dtypes, i32_sub, K, n, cols_out, S(stream));
+  LFE_API_END
+}
+int lfe_uploader_create(lfe_handle h, int64_t chunk_bytes, int n_slots, int n_threads, lfe_uploader_t* out) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && out, "lfe_uploader_create: NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  *out = uploader_create(h, chunk_bytes, n_slots, n_threads);
+  LFE_API_END
+}
+int lfe_uploader_destroy(lfe_uploader_t u) {
+  LFE_API_BEGIN
+  uploader_destroy(u);
+  LFE_API_END
+}
+int lfe_uploader_enqueue(lfe_uploader_t u, const void* host_src, int64_t nbytes, void* dev_dst, void* copy_stream,
+                         int64_t* ticket_out) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(u && ticket_out, "lfe_uploader_enqueue: NULL argument");
+  *ticket_out = uploader_enqueue(u, host_src, nbytes, dev_dst, S(copy_stream));
+  LFE_API_END
+}
+int lfe_uploader_stream_wait(lfe_uploader_t u, int64_t ticket, void* compute_stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(u != nullptr, "lfe_uploader_stream_wait: NULL argument");
+  uploader_stream_wait(u, ticket, S(compute_stream));
+  LFE_API_END
+}
+int lfe_uploader_drain(lfe_uploader_t u) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(u != nullptr, "lfe_uploader_drain: NULL argument");
+  uploader_drain(u);
   LFE_API_END
 }
 int lfe_allreduce_f64(lfe_handle h, double* buf, int64_t count, void* stream) {

@@ -7,7 +7,7 @@ mkdir -p "${OUT}" "${HERE}/build"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -O3
        --expt-relaxed-constexpr -Xptxas -v)
-SRCS=(api prims sort factorize demean gram vcov compress shard)
+SRCS=(api prims sort factorize demean gram vcov compress shard upload)
 pids=()
 for s in "${SRCS[@]}"; do
   if [ ! -f "${HERE}/build/${s}.o" ] || [ "${HERE}/${s}.cu" -nt "${HERE}/build/${s}.o" ] || \
@@ -21,5 +21,5 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 OBJS=()
 for s in "${SRCS[@]}"; do OBJS+=("${HERE}/build/${s}.o"); done
-"${NVCC}" -shared -o "${OUT}/liblfe.so" "${OBJS[@]}" -lcudart -ldl
+"${NVCC}" -shared -o "${OUT}/liblfe.so" "${OBJS[@]}" -lcudart -ldl -lpthread
 echo "built ${OUT}/liblfe.so"

@@ -1258,7 +1258,9 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
                                                                                   S1.nsum, S1.G, Cp, dmax, 0);
       KERNEL_CHECK();
       h->n_launches += 1;
-      if (dist) comm_allreduce(h, dmax, 1, 1, s);
+      // a non-local FE's table comes from all-reduced sums, so its maximum is already the same number on every
+      // rank: no second collective per stopping test (only a rank-local first FE needs the max over ranks)
+      if (dist && fe_order[0] == local_fe) comm_allreduce(h, dmax, 1, 1, s);
       CUDA_CHECK(cudaMemcpyAsync(&max_mean, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
       if (max_mean < tol && F > 2) {
@@ -1277,7 +1279,9 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
           h->n_launches += 1;
         }
         double mid = 0.0;
-        if (dist) comm_allreduce(h, dmax, 1, 1, s);
+        bool local_mid = false;
+        for (int oi = 1; oi + 1 < F; ++oi) local_mid = local_mid || fe_order[oi] == local_fe;
+        if (dist && local_mid) comm_allreduce(h, dmax, 1, 1, s);
         CUDA_CHECK(cudaMemcpyAsync(&mid, dmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
         if (mid > max_mean) max_mean = mid;

@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(256) k_permute_small(const T* __restrict__ src
     dst[r] = src[perm[r]];
 }
 
+__global__ void k_not_u64(unsigned long long* p) { *p = ~*p; }
+
 template <int DT>
 static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int order, int32_t* codes,
                               void* uniques_v, int64_t uniques_cap, cudaStream_t s) {
@@ -230,9 +232,11 @@ static int64_t factorize_impl(lfe_ctx* h, const void* keys_v, int64_t n, int ord
     k_minmax<DT><<<blocks, 256, 0, s>>>(keys, n, mm);
     KERNEL_CHECK();
   }
-  if (global) {  // one code space for all ranks: global key range, merged presence table
-    comm_allreduce_int(h, mm.p, 1, 1, 3, s);
-    comm_allreduce_int(h, mm.p + 1, 1, 1, 2, s);
+  if (global) {  // one code space for all ranks: global key range (ONE max all-reduce of [~min, max]), merged presence table
+    k_not_u64<<<1, 1, 0, s>>>(mm.p);
+    comm_allreduce_int(h, mm.p, 2, 1, 2, s);
+    k_not_u64<<<1, 1, 0, s>>>(mm.p);
+    KERNEL_CHECK();
   }
   unsigned long long hmm[2];
   CUDA_CHECK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, s));
@@ -637,50 +641,54 @@ void singleton_mask_impl(lfe_ctx* h, const int32_t* const* codes, const int64_t*
   DevBuf<unsigned long long> acc(2 + F, s);
   acc.zero();
   int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  std::vector<unsigned long long> hacc(2 + F);
   // No group of size one anywhere (the usual panel) => every row is kept: the row pass is skipped.  The group
-  // tables are G-sized, the row pass N-sized.  With several ranks the number of singleton groups is summed
-  // first so that all ranks take the same branch.
+  // tables are G-sized, the row pass N-sized.  Everything that decision and its results need from the other ranks
+  // -- the number of singleton groups (so that all ranks take the same branch), the global row count and the
+  // shard key's group count -- travels in ONE all-reduce of three counters, read back with one synchronisation;
+  // the non-local FEs' tables are already global, so their counters are the same on every rank.
+  int64_t n_tot = n;
   {
-    DevBuf<unsigned long long> ones(1, s);
-    ones.zero();
+    DevBuf<unsigned long long> red(3, s), nz(F, s);
+    red.zero(); nz.zero();
     for (int j = 0; j < F; ++j) {
-      k_count_ones<<<launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8), 256, 0, s>>>(cnts[j], n_groups[j], ones);
+      const int bg = launch_blocks(h, ceil_div64(n_groups[j], 256 * 4), 8);
+      k_count_ones<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], red.p);
+      KERNEL_CHECK();
+      k_count_nonzero<<<bg, 256, 0, s>>>(cnts[j], n_groups[j], nz.p + j);
       KERNEL_CHECK();
     }
-    h->n_launches += 1;
-    if (dist) comm_allreduce_int(h, ones.p, 1, 1, 0, s);
-    unsigned long long h_ones = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h_ones, ones.p, sizeof(h_ones), cudaMemcpyDeviceToHost, s));
+    h->n_launches += 2;
+    unsigned long long hn = (unsigned long long)n;
+    CUDA_CHECK(cudaMemcpyAsync(red.p + 1, &hn, sizeof(hn), cudaMemcpyHostToDevice, s));   // pageable: staged at once
+    if (dist && local_fe >= 0 && local_fe < F)
+      CUDA_CHECK(cudaMemcpyAsync(red.p + 2, nz.p + local_fe, sizeof(hn), cudaMemcpyDeviceToDevice, s));
+    if (dist) comm_allreduce_int(h, red.p, 3, 1, 0, s);
+    unsigned long long hred[3];
+    std::vector<unsigned long long> hnz(F);
+    CUDA_CHECK(cudaMemcpyAsync(hred, red.p, sizeof(hred), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(hnz.data(), nz.p, F * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    if (h_ones == 0) {
+    n_tot = (int64_t)hred[1];
+    n_keep_out[2] = n_tot;
+    if (hred[0] == 0) {
       if (n > 0) CUDA_CHECK(cudaMemsetAsync(keep, 1, (size_t)n, s));
-      unsigned long long hn[2] = {(unsigned long long)n, (unsigned long long)n};
-      CUDA_CHECK(cudaMemcpyAsync(acc.p, hn, sizeof(hn), cudaMemcpyHostToDevice, s));   // pageable: staged at once
-      blocks = 0;   // skip the row pass below
+      n_keep_out[0] = n;
+      n_keep_out[1] = n_tot;
+      if (fe_dims_out)
+        for (int j = 0; j < F; ++j) fe_dims_out[j] = (int64_t)((dist && j == local_fe) ? hred[2] : hnz[j]);
+      return;
     }
   }
-  if (n > 0 && blocks > 0) {
+  if (n > 0) {
     k_singleton_mask<<<blocks, 256, 0, s>>>(P, F, n, keep, acc);
     KERNEL_CHECK();
     h->n_launches += 1;
   }
   CUDA_CHECK(cudaMemcpyAsync(acc.p + 1, acc.p, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
   if (dist) comm_allreduce_int(h, acc.p + 1, 1, 1, 0, s);
-  std::vector<unsigned long long> hacc(2 + F);
   CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  // rows over all ranks: "did anyone drop a row" must be ONE decision for every rank, here and in the caller
-  int64_t n_tot = n;
-  if (dist) {
-    DevBuf<unsigned long long> nt(1, s);
-    unsigned long long hn = (unsigned long long)n;
-    CUDA_CHECK(cudaMemcpyAsync(nt.p, &hn, sizeof(hn), cudaMemcpyHostToDevice, s));
-    comm_allreduce_int(h, nt.p, 1, 1, 0, s);
-    CUDA_CHECK(cudaMemcpyAsync(&hn, nt.p, sizeof(hn), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    n_tot = (int64_t)hn;
-  }
-  n_keep_out[2] = n_tot;
   if (fe_dims_out) {
     const bool dropped = (int64_t)hacc[1] < n_tot;
     for (int j = 0; j < F; ++j) {

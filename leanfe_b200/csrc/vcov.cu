@@ -516,6 +516,8 @@ __global__ void __launch_bounds__(TL_T) k_tail_resid(TailCols cols, TailTabs T, 
   }
 }
 
+__global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, double* __restrict__ out) { *out = (double)*in; }
+
 __global__ void __launch_bounds__(256) k_meat_final(const double* __restrict__ partials, int nblocks, int K,
                                                     double* __restrict__ out) {
   const int NT = K * (K + 1) / 2;
@@ -604,14 +606,45 @@ void resid_vcov_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t
   } else {
     raw.zero();
   }
-  if (h->world > 1) comm_allreduce(h, raw, 4, 0, s);
+  // Everything the ranks must combine is summed in ONE all-reduce of pack = [raw moments (4) | #clusters (1) | meat
+  // (k x k)]: the meat is additive over ranks for HC1 and for rank-local clusters (cluster == shard key); clusters
+  // shared by ranks need their score table summed first (a second, G x k collective).
+  const bool dist = h->world > 1;
+  DevBuf<double> pack((size_t)5 + (size_t)k * k, s);
+  pack.zero();
+  CUDA_CHECK(cudaMemcpyAsync(pack.p, raw.p, 4 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  double* meat = pack.p + 5;
   double* stats = stats_out ? stats_out : stats_local.p;
-  k_stats_from_raw<<<1, 32, 0, s>>>(raw, (double)n_obs, stats);
+  DevBuf<double> V((size_t)(k > 0 ? k * k : 1), s), tmp((size_t)(k > 0 ? k * k : 1), s);
+  V.zero();
+  if (k > 0 && vcov_kind == LFE_VCOV_HC1 && n > 0) {
+    k_meat_final<<<1, 256, 0, s>>>(meat_partials, blocks, k, meat);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  }
+  if (k > 0 && vcov_kind == LFE_VCOV_CLUSTER) {
+    if (dist && !cl_local) {
+      comm_allreduce_int(h, present.p, Gcap, 0, 2, s);
+      comm_allreduce(h, S, Gcap * ldS, 0, s);
+    }
+    k_sum_u32<<<launch_blocks(h, ceil_div64(Gcap, 1024), 8), 256, 0, s>>>(present, Gcap, tot);
+    KERNEL_CHECK();
+    k_u64_to_f64<<<1, 1, 0, s>>>(tot, pack.p + 4);
+    KERNEL_CHECK();
+    std::vector<const double*> sc(k);
+    for (int c = 0; c < k; ++c) sc[c] = S.p + c;
+    gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, ldS);
+    h->n_launches += 2;
+    if (dist && !cl_local) {
+      // the table is already global: every rank holds the full meat and count; keep one copy in the sum below
+      if (h->rank != 0) CUDA_CHECK(cudaMemsetAsync(pack.p + 4, 0, (size_t)(1 + k * k) * sizeof(double), s));
+    }
+  }
+  if (dist) comm_allreduce(h, pack, 5 + (int64_t)k * k, 0, s);
+  k_stats_from_raw<<<1, 32, 0, s>>>(pack, (double)n_obs, stats);
   KERNEL_CHECK();
   h->n_launches += 2;
   if (k == 0) return;
-  DevBuf<double> V((size_t)k * k, s), tmp((size_t)k * k, s), meat((size_t)k * k, s);
-  V.zero();
   if (vcov_kind == LFE_VCOV_IID) {
     CUDA_CHECK(cudaMemcpyAsync(V.p, Binv, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
     k_scale_se<<<1, 256, 0, s>>>(V, k, 1.0, stats, 2, (double)df_resid, vcov_out, se_out);
@@ -619,44 +652,25 @@ void resid_vcov_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t
     h->n_launches += 1;
     return;
   }
-  if (vcov_kind == LFE_VCOV_HC1) {
-    if (n > 0) {
-      k_meat_final<<<1, 256, 0, s>>>(meat_partials, blocks, k, meat);
-      KERNEL_CHECK();
-    } else {
-      meat.zero();
-    }
-    if (h->world > 1) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
-    k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
-    KERNEL_CHECK();
-    k_scale_se<<<1, 256, 0, s>>>(V, k, (double)n_obs / (double)df_resid, nullptr, 0, 1.0, vcov_out, se_out);
-    KERNEL_CHECK();
-    h->n_launches += 3;
-    return;
-  }
-  // one-way cluster: number of clusters with at least one row, meat = S'S
-  if (h->world > 1 && !cl_local) comm_allreduce_int(h, present.p, Gcap, 0, 2, s);
-  k_sum_u32<<<launch_blocks(h, ceil_div64(Gcap, 1024), 8), 256, 0, s>>>(present, Gcap, tot);
-  KERNEL_CHECK();
-  if (h->world > 1 && cl_local) comm_allreduce_int(h, tot.p, 1, 1, 0, s);
-  unsigned long long ht = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&ht, tot.p, sizeof(ht), cudaMemcpyDeviceToHost, s));
-  if (h->world > 1 && !cl_local) comm_allreduce(h, S, Gcap * ldS, 0, s);
-  std::vector<const double*> sc(k);
-  for (int c = 0; c < k; ++c) sc[c] = S.p + c;
-  gram_core(h, sc.data(), k, Gcap, nullptr, nullptr, 0, meat, s, ldS);
-  if (h->world > 1 && cl_local) comm_allreduce(h, meat, (int64_t)k * k, 0, s);
   k_sandwich<<<1, 256, 0, s>>>(Binv, meat, k, 1.0, tmp, V);
   KERNEL_CHECK();
+  if (vcov_kind == LFE_VCOV_HC1) {
+    k_scale_se<<<1, 256, 0, s>>>(V, k, (double)n_obs / (double)df_resid, nullptr, 0, 1.0, vcov_out, se_out);
+    KERNEL_CHECK();
+    h->n_launches += 2;
+    return;
+  }
+  double hG = 0.0;
+  CUDA_CHECK(cudaMemcpyAsync(&hG, pack.p + 4, sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  const int64_t G = (int64_t)ht;
+  const int64_t G = (int64_t)(hG + 0.5);
   if (n_clusters_out) n_clusters_out[0] = G;
   LFE_REQUIRE(G > 1, "clustered vcov: a single cluster (division by zero in G/(G-1))");
   double adj = (double)G / (double)(G - 1);
   if (ssc) adj *= (double)(n_obs - 1) / (double)df_resid;
   k_scale_se<<<1, 256, 0, s>>>(V, k, adj, nullptr, 0, 1.0, vcov_out, se_out);
   KERNEL_CHECK();
-  h->n_launches += 4;
+  h->n_launches += 2;
 }
 
 void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, const double* beta_full,

@@ -42,6 +42,9 @@ class Engine:
             self.set_profiling(True)
 
     def close(self):
+        if getattr(self, "_uploader", None) is not None:
+            self.lib.lfe_uploader_destroy(self._uploader)
+            self._uploader = None
         if getattr(self, "h", None):
             self.lib.lfe_destroy(self.h)
             self.h = None
@@ -62,6 +65,36 @@ class Engine:
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         return self._copy_stream
+
+    def host_uploader(self):
+        """The native pageable-memory uploader of this engine (lfe_uploader_*: pinned ring + staging threads),
+        created on first use: 8 x 32 MB pinned slots; LFE_UPLOAD_THREADS staging threads (default: a share of the
+        host's cores, so that one rank per GPU does not oversubscribe the box)."""
+        if getattr(self, "_uploader", None) is None:
+            import os
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except Exception:
+                cores = os.cpu_count() or 4
+            ranks = max(torch.cuda.device_count() if self.world > 1 else 1, 1)
+            threads = int(os.environ.get("LFE_UPLOAD_THREADS", max(2, min(8, cores // (2 * ranks) or 1))))
+            u = C.c_void_p()
+            capi.check(self.lib.lfe_uploader_create(self.h, 32 << 20, 8, threads, C.byref(u)))
+            self._uploader = u
+        return self._uploader
+
+    def upload_enqueue(self, host_ptr: int, nbytes: int, dst: torch.Tensor, copy_stream) -> int:
+        t = C.c_int64(0)
+        capi.check(self.lib.lfe_uploader_enqueue(self.host_uploader(), C.c_void_p(host_ptr), int(nbytes), self._p(dst),
+                                                 C.c_void_p(copy_stream.cuda_stream), C.byref(t)))
+        return int(t.value)
+
+    def upload_wait(self, ticket: int, compute_stream):
+        capi.check(self.lib.lfe_uploader_stream_wait(self.host_uploader(), int(ticket), C.c_void_p(compute_stream.cuda_stream)))
+
+    def upload_drain(self):
+        if getattr(self, "_uploader", None) is not None:
+            capi.check(self.lib.lfe_uploader_drain(self._uploader))
 
     def empty(self, n, dtype):
         return torch.empty(int(n), dtype=dtype, device=self.device)

@@ -70,13 +70,19 @@ def _arrow_to_numpy(chunked):
     return arr.to_numpy(zero_copy_only=False)
 
 
-class Uploader:
-    """All host->device copies of a fit, enqueued up front on a dedicated copy stream.
+_NP_TO_TORCH = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.int64): torch.int64,
+                np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8}
 
-    Key columns go first so that factorisation, the singleton test and the entry-list sorts (which need only
-    the ids) run while the fp64 columns are still crossing PCIe; the compute stream waits on a per-column
-    event right before a column's first use.  With pinned host tensors the copies are truly asynchronous;
-    with pageable memory the driver stages them synchronously and this degrades to the plain ordering.
+
+class Uploader:
+    """All host->device copies of a fit, enqueued up front, key columns first, so that factorisation, the singleton
+    test and the entry-list sorts (which need only the ids) run while the fp64 columns are still crossing PCIe; the
+    compute stream waits on a per-column event right before a column's first use.
+
+    Pinned host tensors are copied with one asynchronous ``copy_`` each on the engine's copy stream.  PAGEABLE
+    sources -- NumPy arrays, pandas / Arrow columns, unpinned tensors: what the reference API receives
+    (polars_impl.py:342-347) -- go through the library's pinned ring (``lfe_uploader_*``, csrc/upload.cu): host
+    threads stage 32 MB chunks, one cudaMemcpyAsync per chunk; read-only sources are read where they lie.
     """
 
     def __init__(self, eng: Engine, frame: Frame, names: list[str]):
@@ -84,14 +90,19 @@ class Uploader:
         self.compute = torch.cuda.current_stream(eng.device)
         self.copy = None
         self.dev: dict[str, torch.Tensor] = {}
-        self.events: dict[str, torch.cuda.Event] = {}
+        self.events: dict[str, object] = {}    # name -> torch Event (pinned path) or int ticket (pinned-ring path)
         self._host_refs: list = []
+        self._ring_used = False
         self.events_seen: set[str] = set()     # columns whose device copy was made here (never caller-owned)
-        pending = []
+        jobs = []
         for name in dict.fromkeys(names):
             col = frame.column(name)
             if isinstance(col, torch.Tensor):
-                t = col
+                if col.is_cuda:
+                    self.dev[name] = col.contiguous()
+                    continue
+                t = col.contiguous()
+                jobs.append((name, t, t.dtype, tuple(t.shape), t.data_ptr() if not t.is_pinned() else None))
             elif _is_stringlike(col):
                 continue                                   # dictionary-encoded on the host at first use
             else:
@@ -102,38 +113,50 @@ class Uploader:
                     a = a.astype(np.int32)
                 elif a.dtype == np.float16:
                     a = a.astype(np.float32)
-                if not a.flags.writeable:
-                    a = a.copy()
-                t = torch.from_numpy(np.ascontiguousarray(a))
-            if t.is_cuda:
-                self.dev[name] = t.contiguous()
-                continue
-            # destination allocated on the COMPUTE stream (so the caching allocator reuses the previous fit's
-            # blocks instead of growing a per-copy-stream pool), filled on the engine's one copy stream
-            t = t.contiguous()
-            d = torch.empty(t.shape, dtype=t.dtype, device=eng.device)
-            pending.append((name, t, d))
-        if pending:
+                a = np.ascontiguousarray(a)                # no-op for the usual contiguous column
+                if a.dtype in _NP_TO_TORCH:
+                    jobs.append((name, a, _NP_TO_TORCH[a.dtype], a.shape, a.ctypes.data))
+                else:                                      # exotic dtype: let torch convert (needs a writable array)
+                    t = torch.from_numpy(a if a.flags.writeable else a.copy())
+                    jobs.append((name, t, t.dtype, tuple(t.shape), t.data_ptr()))
+        if jobs:
             self.copy = eng.copy_stream()
             self.copy.wait_stream(self.compute)
-            with torch.cuda.stream(self.copy):
-                for name, t, d in pending:
-                    d.copy_(t, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy)
-                    d.record_stream(self.copy)
-                    self.dev[name], self.events[name] = d, ev
-                    self.events_seen.add(name)
-                    self._host_refs.append(t)              # keep the source alive until the async copy ran
+            for name, src, dtype, shape, ptr in jobs:
+                # destination allocated on the COMPUTE stream (so the caching allocator reuses the previous fit's
+                # blocks instead of growing a per-copy-stream pool), filled on the engine's one copy stream
+                d = torch.empty(shape, dtype=dtype, device=eng.device)
+                d.record_stream(self.copy)
+                if ptr is None:                            # pinned tensor: one truly asynchronous copy
+                    with torch.cuda.stream(self.copy):
+                        d.copy_(src, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy)
+                    self.events[name] = ev
+                else:                                      # pageable: the library's pinned ring
+                    self.events[name] = eng.upload_enqueue(ptr, d.numel() * d.element_size(), d, self.copy)
+                    self._ring_used = True
+                self.dev[name] = d
+                self.events_seen.add(name)
+                self._host_refs.append(src)                # keep the source alive until its copy ran
 
     def get(self, name: str):
         """Device tensor of an uploaded column (compute stream ordered after its copy), else the host column."""
         if name in self.dev:
             ev = self.events.pop(name, None)
-            if ev is not None:
+            if isinstance(ev, int):
+                self.eng.upload_wait(ev, self.compute)
+            elif ev is not None:
                 self.compute.wait_event(ev)
             return self.dev[name]
         return self.frame.column(name)
+
+    def close(self):
+        """End of the fit: every ring job has completed before the host sources may go away."""
+        if self._ring_used:
+            self.eng.upload_drain()
+            self._ring_used = False
+        self._host_refs.clear()
 
 
 @dataclass

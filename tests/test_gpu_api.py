@@ -315,3 +315,38 @@ def test_wide_design_twenty_regressors():
     for vc, cl in (("iid", None), ("hc1", None), ("cluster", ["f2"])):
         res = leanfe(d, formula=f, vcov=vc, cluster_cols=cl)
         _check(res, O.leanfe_oracle(d, formula=f, vcov=vc, cluster_cols=cl))
+
+
+def test_pageable_ingest_ring_is_bit_exact_for_every_source_kind():
+    """lfe_uploader_* (pinned ring + staging threads): the bytes that arrive are the bytes that were sent -- columns
+    larger than the whole ring (8 x 32 MB), odd sizes, read-only arrays, narrow dtypes, unpinned tensors -- and the
+    fit from such sources equals the fit from device tensors."""
+    from leanfe_b200 import leanfe
+    from leanfe_b200.engine import get_engine
+    from leanfe_b200.frontend import Frame, Uploader
+    eng = get_engine(0)
+    rng = np.random.default_rng(3)
+    big = rng.integers(-2**62, 2**62, 40_000_003)                      # 320 MB > 256 MB of ring
+    ro = rng.normal(size=1_000_001)
+    ro.setflags(write=False)
+    cols = {"big": big, "ro": ro, "u8": rng.integers(0, 255, 70_001).astype(np.uint8),
+            "f32": rng.normal(size=33).astype(np.float32), "i32": rng.integers(-9, 9, 5_000_000).astype(np.int32),
+            "unpinned": torch.from_numpy(rng.normal(size=2_000_003)), "strided": rng.normal(size=(100_000, 3))[:, 1],
+            "pinned": torch.from_numpy(rng.normal(size=300_001)).pin_memory(), "empty": np.zeros(0)}
+    up = Uploader(eng, Frame(cols, list(cols)), list(cols))
+    for name, src in cols.items():
+        got = up.get(name)
+        exp = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.array(src)))
+        assert got.is_cuda and got.dtype == exp.dtype and torch.equal(got.cpu(), exp), name
+    up.close()
+    # the public API on pageable / read-only inputs
+    n = 400_000
+    d = dict(y=rng.normal(size=n), x=rng.normal(size=n), f=rng.integers(0, 5000, n), g=rng.integers(0, 7, n))
+    base = leanfe({k: torch.from_numpy(v).cuda() for k, v in d.items()}, formula="y ~ x | f + g", vcov="cluster",
+                  cluster_cols=["f"])
+    for v in d.values():
+        v.setflags(write=False)
+    for _ in range(3):                                                  # ring slots are reused across fits
+        r = leanfe(d, formula="y ~ x | f + g", vcov="cluster", cluster_cols=["f"])
+        assert r.coefs["x"] == pytest.approx(base.coefs["x"], rel=1e-12)
+        assert r.std_errors["x"] == pytest.approx(base.std_errors["x"], rel=1e-12)
