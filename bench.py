@@ -15,7 +15,9 @@ time-FE tables, Gram and meat are all-reduced over NCCL inside liblfe.  Before t
 run checks the sharded fits against the single-process oracle (`mg_parity`), and every run adds a
 `c5_strong` record: BASELINE config 5 (400M rows, 10 regressors, two-way FE) generated on the device by a
 counter-based RNG keyed by the GLOBAL row index -- the same panel at every N -- split into arbitrary
-(contiguous-index) row shards that the library repartitions by unit itself.
+(contiguous-index) row shards that the library repartitions by unit itself; `c3_akm` (config 3: 100M rows,
+worker + firm + year, HC1) and `c4_yoco` (config 4: 200M rows, 23 dummies, strategy='compress', clustered) are
+measured the same way, so every named shape has a driver-visible line at 1, 2, 4 and 8 GPUs.
 
 The CPU arm (`cpu_baseline`, `--impl reference`) fits the SAME full panel on all host cores: the real
 reference through Polars when `import polars` works on the box, else the OpenMP C port of its algorithm
@@ -132,6 +134,58 @@ def make_c5_rows(torch, dev, lo: int, hi: int, n_total: int, chunk: int = 25_000
         out["unit"][sl] = unit
         out["time"][sl] = tm
     return out
+
+
+def make_c3_rows(torch, dev, lo: int, hi: int, n_total: int, chunk: int = 25_000_000):
+    """Rows [lo, hi) of the c3 AKM panel: worker ~ U{0..N/10}, each worker has a home firm, 80 % of its
+    rows are at home and 20 % at a random firm (N/100 firms), year ~ U{0..30}; k = 2.  Pure function of the global
+    row index (and of the worker / firm id for the effects)."""
+    nw, nf = max(n_total // 10, 10), max(n_total // 100, 5)
+    n = hi - lo
+    out = {nm: torch.empty(n, dtype=torch.float64, device=dev) for nm in ("y", "x1", "x2")}
+    for nm in ("worker", "firm", "year"):
+        out[nm] = torch.empty(n, dtype=torch.int64, device=dev)
+    for a in range(lo, hi, chunk):
+        b = min(a + chunk, hi)
+        sl = slice(a - lo, b - lo)
+        idx = torch.arange(a, b, dtype=torch.int64, device=dev)
+        worker = (_uniform(torch, idx, 1) * nw).to(torch.int64).clamp_(max=nw - 1)
+        home = (_uniform(torch, worker, 60) * nf).to(torch.int64).clamp_(max=nf - 1)
+        firm = torch.where(_uniform(torch, idx, 2) >= 0.8, (_uniform(torch, idx, 3) * nf).to(torch.int64).clamp_(max=nf - 1), home)
+        year = (_uniform(torch, idx, 4) * 30).to(torch.int64).clamp_(max=29)
+        aw, af = _normal(torch, worker, 61), _normal(torch, firm, 62)
+        x1 = _normal(torch, idx, 101) + 0.3 * aw
+        x2 = _normal(torch, idx, 102) + 0.2 * af
+        out["y"][sl] = 0.8 * x1 - 0.3 * x2 + aw + af + 0.05 * year + _normal(torch, idx, 52)
+        out["x1"][sl], out["x2"][sl] = x1, x2
+        out["worker"][sl], out["firm"][sl], out["year"][sl] = worker, firm, year
+    return out
+
+
+def make_c4_rows(torch, dev, lo: int, hi: int, chunk: int = 25_000_000):
+    """Rows [lo, hi) of the c4 event-study panel (after docs/tutorials/did.qmd:25-103): group ~ U{0..1000},
+    period ~ U{0..24}, 40 % of the groups treated from period 12; 23 uint8 dummies treated x 1[period = t], t != 11."""
+    n = hi - lo
+    out = {"y": torch.empty(n, dtype=torch.float64, device=dev), "group": torch.empty(n, dtype=torch.int64, device=dev),
+           "period": torch.empty(n, dtype=torch.int64, device=dev)}
+    names = [f"d{t}" for t in range(24) if t != 11]
+    for nm in names:
+        out[nm] = torch.empty(n, dtype=torch.uint8, device=dev)
+    ar = torch.arange(24, device=dev)
+    eff = torch.where(ar >= 12, 0.5 + 0.05 * (ar - 12), 0.0).double()
+    for a in range(lo, hi, chunk):
+        b = min(a + chunk, hi)
+        sl = slice(a - lo, b - lo)
+        idx = torch.arange(a, b, dtype=torch.int64, device=dev)
+        grp = (_uniform(torch, idx, 1) * 1000).to(torch.int64).clamp_(max=999)
+        per = (_uniform(torch, idx, 2) * 24).to(torch.int64).clamp_(max=23)
+        treated = grp < 400
+        out["y"][sl] = _normal(torch, grp, 70) + _normal(torch, per, 71) + treated * eff[per] + _normal(torch, idx, 52)
+        out["group"][sl], out["period"][sl] = grp, per
+        for t in range(24):
+            if t != 11:
+                out[f"d{t}"][sl] = (treated & (per == t)).to(torch.uint8)
+    return out, names
 
 
 class ClockSampler:
@@ -297,7 +351,10 @@ def main():
     ap.add_argument("--c5-rows", type=int, default=400_000_000, help="TOTAL rows of the c5 strong-scaling record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arms (profiling runs)")
+    ap.add_argument("--c3-rows", type=int, default=100_000_000, help="TOTAL rows of the c3 (AKM, 3-way FE) record")
+    ap.add_argument("--c4-rows", type=int, default=200_000_000, help="TOTAL rows of the c4 (YOCO) record")
     ap.add_argument("--no-c5", action="store_true", help="skip the c5 strong-scaling record")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 records")
     ap.add_argument("--no-mg-parity", action="store_true", help="skip the multi-GPU oracle check (world > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -459,42 +516,68 @@ def main():
     if world > 1:
         del d
 
-    # ---- c5 strong scaling: the SAME 400M-row panel at every N, arbitrary row shards in -----------------
-    c5 = None
-    if not args.no_c5:
-        torch.cuda.empty_cache()
-        n5 = args.c5_rows
-        lo5, hi5 = n5 * rank // world, n5 * (rank + 1) // world
-        shard5 = make_c5_rows(torch, dev, lo5, hi5, n5)
-        kw5 = dict(formula=C5_FORMULA, vcov="cluster", cluster_cols=["unit"], strategy="alt_proj")
-        r5 = leanfe(shard5, **kw5)       # warm-up (NCCL all-to-all buffers, pool growth)
+    # ---- the other named shapes, strong scaling: the SAME panel at every N, arbitrary row shards in ---------
+    def strong_record(label, shard, kw_fit, n_tot, steps_s=2):
+        """Fit `shard` (this rank's contiguous-global-row-index block of an n_tot-row panel) steps_s times; the
+        library repartitions the rows by the highest-cardinality FE inside the timed region."""
+        r = leanfe(shard, **kw_fit)       # warm-up (NCCL all-to-all buffers, pool growth)
         eng.set_profiling(True)
         eng.reset_timers()
         barrier()
-        steps5 = 2
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        for _ in range(steps5):
-            r5 = leanfe(shard5, **kw5)
+        for _ in range(steps_s):
+            r = leanfe(shard, **kw_fit)
         a1.record()
         barrier()
-        ms5 = a0.elapsed_time(a1) / steps5
-        t5 = eng.timers()
+        ms_s = a0.elapsed_time(a1) / steps_s
+        tm = eng.timers()
+        cn = eng.counters()
         eng.set_profiling(False)
         if world > 1:
-            tt = torch.tensor([ms5], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms5 = float(tt[0])
-        c5 = {"workload": f"c5: {n5 // 1_000_000}M rows TOTAL, 10 regressors | unit({n5 // C5_ROWS_PER_UNIT}) + time(500), "
-                          "cluster(unit); identical panel at every N (counter-based RNG keyed by global row index)",
-              "scaling": "strong", "n_gpus": world, "rows_total": n5, "ms_per_fit": ms5, "value": n5 / (ms5 / 1e3),
-              "unit": "rows/s", "input": "device-resident, rows sharded by contiguous global row index (arbitrary w.r.t. unit); "
-              "the library repartitions by unit (lfe_shard_plan / lfe_shard_exchange) inside the timed region",
-              "sweeps": r5.iterations, "n_obs": r5.n_obs,
-              "phases_ms_per_fit": {k_: round(v / steps5, 3) for k_, v in t5.items() if v > 0},
-              "coefs": {k_: float(v) for k_, v in r5.coefs.items()},
-              "std_errors": {k_: float(v) for k_, v in r5.std_errors.items()}}
+            tt_ = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            ms_s = float(tt_[0])
+        return {"workload": label + "; identical panel at every N (counter-based RNG keyed by the global row index)",
+                "scaling": "strong", "n_gpus": world, "rows_total": n_tot, "ms_per_fit": ms_s, "value": n_tot / (ms_s / 1e3),
+                "unit": "rows/s", "input": "device-resident; rank r holds global rows [r N/W, (r+1) N/W) -- arbitrary with "
+                "respect to every fixed effect" + ("" if world == 1 else "; the library's repartition / partial-table merge "
+                                                   "runs inside the timed region"),
+                "sweeps": r.iterations, "converged": r.converged, "n_obs": r.n_obs, "strategy": r.strategy,
+                "n_compressed": r.n_compressed, "collectives_per_fit": cn["collectives"] / steps_s,
+                "phases_ms_per_fit": {k_: round(v / steps_s, 3) for k_, v in tm.items() if v > 0},
+                "coefs": {k_: float(v) for k_, v in list(r.coefs.items())[:10]},
+                "std_errors": {k_: float(v) for k_, v in list(r.std_errors.items())[:10]}}
+
+    c5 = c3 = c4 = None
+    if not args.no_c5:
+        torch.cuda.empty_cache()
+        n5 = args.c5_rows
+        shard5 = make_c5_rows(torch, dev, n5 * rank // world, n5 * (rank + 1) // world, n5)
+        c5 = strong_record(f"c5: {n5 // 1_000_000}M rows TOTAL, 10 regressors | unit({n5 // C5_ROWS_PER_UNIT}) + time(500), iid",
+                           shard5, dict(formula=C5_FORMULA, vcov="iid", strategy="alt_proj"), n5)
         del shard5
+        torch.cuda.empty_cache()
+    if not args.no_extra:
+        n3 = args.c3_rows
+        shard3 = make_c3_rows(torch, dev, n3 * rank // world, n3 * (rank + 1) // world, n3)
+        c3 = strong_record(f"c3: AKM {n3 // 1_000_000}M rows TOTAL, 2 regressors | worker({n3 // 10}) + firm({n3 // 100}) + "
+                           "year(30), HC1, 50 sweeps", shard3,
+                           dict(formula="y ~ x1 + x2 | worker + firm + year", vcov="hc1", strategy="alt_proj"), n3)
+        # in-place-equivalent sweep rate (SURVEY 8d: N F (16 C + 8) bytes per sweep of the reference's formulation)
+        sw_ms = (c3["phases_ms_per_fit"].get("demean_sweeps", 0) + c3["phases_ms_per_fit"].get("demean_check", 0)) / max(c3["sweeps"], 1)
+        if sw_ms > 0:
+            c3["sweep_ms"] = sw_ms
+            c3["sweep_inplace_equivalent_gbs_all_gpus"] = n3 * 3 * (16 * 3 + 8) / (sw_ms / 1e3) / 1e9
+        del shard3
+        torch.cuda.empty_cache()
+        n4 = args.c4_rows
+        shard4, dnames = make_c4_rows(torch, dev, n4 * rank // world, n4 * (rank + 1) // world)
+        c4 = strong_record(f"c4: YOCO {n4 // 1_000_000}M rows TOTAL, 23 treatment x period dummies | group(1000) + period(24), "
+                           "cluster(group)", shard4,
+                           dict(formula="y ~ " + " + ".join(dnames) + " | group + period", vcov="cluster",
+                                cluster_cols=["group"], strategy="compress"), n4, steps_s=3)
+        del shard4
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -569,6 +652,10 @@ def main():
         out["mg_parity"] = mg_parity
     if c5 is not None:
         out["c5_strong"] = c5
+    if c3 is not None:
+        out["c3_akm"] = c3
+    if c4 is not None:
+        out["c4_yoco"] = c4
     if world == 1 and not args.no_cpu_baseline:
         ds, ns = sample_for_cpu(d, G1, cpu_rows)
         r = cpu_reference_run(ds, 1, 1)
