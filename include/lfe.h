@@ -281,6 +281,14 @@ int lfe_shard_plan(lfe_handle h, const int32_t* codes, int64_t n, int64_t n_grou
 int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_counts /*[host]*/,
                        const int64_t* recv_counts /*[host]*/, const void* const* cols_in, const int* dtypes,
                        const int64_t* i32_sub /*[host], nullable*/, int K, int64_t n, void* const* cols_out, void* stream);
+/* ---- factor / interaction expansion -----------------------------------------------------------------------
+ * Replaces: _expand_factors_polars and _expand_interactions_polars, polars_impl.py:27-115 (one `when(col == cat)`
+ * expression per level).  out_cols[j][i] = (codes[i] == levels[j]) * (base ? base[i] : 1): all J dummy columns of
+ * `i(var)` (base NULL) or `var:i(factor)` (base = var) in ONE pass over the codes.  levels [host] J = the codes of
+ * the non-reference categories; out_dtype LFE_F64, or LFE_U8 for base-less dummies (YOCO groups on raw bytes). */
+int lfe_expand_dummies(lfe_handle h, const int32_t* codes, int64_t n, const int32_t* levels /*[host]*/, int J,
+                       const double* base /*nullable*/, int out_dtype, void* const* out_cols, void* stream);
+
 /* ---- host ingest: pageable memory -> device -------------------------------------------------
  * The reference's API receives DataFrames / NumPy columns (polars_impl.py:342-347): pageable host memory, which a
  * plain cudaMemcpyAsync stages synchronously on one driver thread.  The uploader owns a ring of `n_slots` pinned

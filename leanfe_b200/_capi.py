@@ -29,7 +29,7 @@ EXPORTS = [
     "lfe_demean_plan_destroy", "lfe_demean_plan_fit", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
     "lfe_allreduce_f64", "lfe_shard_plan", "lfe_shard_exchange",
-    "lfe_uploader_create", "lfe_uploader_destroy", "lfe_uploader_enqueue", "lfe_uploader_stream_wait", "lfe_uploader_drain",
+    "lfe_expand_dummies", "lfe_uploader_create", "lfe_uploader_destroy", "lfe_uploader_enqueue", "lfe_uploader_stream_wait", "lfe_uploader_drain",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
     lib.lfe_comm_set_active.argtypes = [vp, i32]
     lib.lfe_compress_merge.argtypes = [vp, P(vp), P(i64), i32, vp, vp, vp, vp, i64, i64, P(vp), vp, vp, vp, vp, P(i64), vp]
     lib.lfe_allreduce_f64.argtypes = [vp, vp, i64, vp]
+    lib.lfe_expand_dummies.argtypes = [vp, vp, i64, P(i32), i32, vp, i32, P(vp), vp]
     lib.lfe_uploader_create.argtypes = [vp, i64, i32, i32, P(vp)]
     lib.lfe_uploader_destroy.argtypes = [vp]
     lib.lfe_uploader_enqueue.argtypes = [vp, vp, i64, vp, vp, P(i64)]

@@ -206,18 +206,15 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             for var, factor, ref in interactions:
                 kc = key(factor, labels=True)
                 ref_cat = resolve_reference(kc.labels, ref, factor)
-                base = num(var)
-                for j, cat in enumerate(kc.labels):
-                    if cat != ref_cat:
-                        X_.append(base * (kc.codes == j))
-                        names.append(f"{var}_{cat}")
+                lv = [j for j, cat in enumerate(kc.labels) if cat != ref_cat]
+                X_ += eng.expand_dummies(kc.codes, lv, base=num(var))          # one pass for all levels
+                names += [f"{var}_{kc.labels[j]}" for j in lv]
             for var, ref in factor_vars:
                 kc = key(var, labels=True)
                 ref_cat = resolve_reference(kc.labels, ref, var)
-                for j, cat in enumerate(kc.labels):
-                    if cat != ref_cat:
-                        X_.append((kc.codes == j).to(torch.uint8 if keep_int else torch.float64))
-                        names.append(f"{var}_{cat}")
+                lv = [j for j, cat in enumerate(kc.labels) if cat != ref_cat]
+                X_ += eng.expand_dummies(kc.codes, lv, as_uint8=keep_int)
+                names += [f"{var}_{kc.labels[j]}" for j in lv]
             # instruments ride along as extra columns: they are demeaned with y and X (polars_impl.py:431, 486); an
             # exogenous regressor listed among the instruments is the same column, demeaned once
             iv_state["k"] = len(names)

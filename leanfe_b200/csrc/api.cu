@@ -195,6 +195,8 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
                          const void* const* cols_in, const int* dtypes, const int64_t* i32_sub, int K, int64_t n,
                          void* const* cols_out, cudaStream_t s);
 
+void expand_dummies_impl(lfe_ctx* h, const int32_t* codes, int64_t n, const int32_t* levels, int J, const double* base,
+                         int out_dtype, void* const* out_cols, cudaStream_t s);
 struct lfe_uploader;
 lfe_uploader* uploader_create(lfe_ctx* h, int64_t chunk_bytes, int n_slots, int n_threads);
 void uploader_destroy(lfe_uploader* u);
@@ -531,6 +533,14 @@ int lfe_shard_exchange(lfe_handle h, const int32_t* order, const int64_t* send_c
               "lfe_shard_exchange: NULL argument");
   CUDA_CHECK(cudaSetDevice(h->device));
   shard_exchange_impl(h, order, send_counts, recv_counts, cols_in, dtypes, i32_sub, K, n, cols_out, S(stream));
+  LFE_API_END
+}
+int lfe_expand_dummies(lfe_handle h, const int32_t* codes, int64_t n, const int32_t* levels, int J, const double* base,
+                       int out_dtype, void* const* out_cols, void* stream) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h && (J == 0 || (levels && out_cols)) && (codes || n == 0) && J >= 0, "lfe_expand_dummies: NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  expand_dummies_impl(h, codes, n, levels, J, base, out_dtype, out_cols, S(stream));
   LFE_API_END
 }
 int lfe_uploader_create(lfe_handle h, int64_t chunk_bytes, int n_slots, int n_threads, lfe_uploader_t* out) {

@@ -309,3 +309,42 @@ void prim_f64_to_u32(lfe_ctx* h, const double* in, int64_t n, uint32_t* out, cud
   KERNEL_CHECK();
   h->n_launches += 1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// factor / interaction expansion: out_j[i] = (code[i] == level_j) * (base ? base[i] : 1)
+// Replaces the per-level column expressions of _expand_factors_polars / _expand_interactions_polars
+// (python/leanfe/polars_impl.py:27-115): one pass reads the code (and base) of a row once and writes all J dummy
+// columns, N (4 + 8 + w J) bytes instead of J passes of compare + multiply.
+// ---------------------------------------------------------------------------------------------
+constexpr int XP_MAXJ = 32;
+struct ExpandSpec {
+  int32_t level[XP_MAXJ];
+  void* out[XP_MAXJ];
+  int J;
+};
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_expand_dummies(const int32_t* __restrict__ code, const double* __restrict__ base,
+                                                        int64_t n, ExpandSpec sp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = __ldcs(code + i);
+    const double b = base ? __ldcs(base + i) : 1.0;
+    for (int j = 0; j < sp.J; ++j) __stcs(reinterpret_cast<OutT*>(sp.out[j]) + i, c == sp.level[j] ? (OutT)b : (OutT)0);
+  }
+}
+
+void expand_dummies_impl(lfe_ctx* h, const int32_t* codes, int64_t n, const int32_t* levels, int J, const double* base,
+                         int out_dtype, void* const* out_cols, cudaStream_t s) {
+  LFE_REQUIRE(out_dtype == LFE_F64 || (out_dtype == LFE_U8 && base == nullptr),
+              "lfe_expand_dummies: outputs are float64, or uint8 for plain (base-less) dummies");
+  if (n <= 0) return;
+  const int blocks = launch_blocks(h, ceil_div64(n, 256 * 4), 8);
+  for (int j0 = 0; j0 < J; j0 += XP_MAXJ) {
+    ExpandSpec sp;
+    sp.J = J - j0 < XP_MAXJ ? J - j0 : XP_MAXJ;
+    for (int j = 0; j < sp.J; ++j) { sp.level[j] = levels[j0 + j]; sp.out[j] = out_cols[j0 + j]; }
+    if (out_dtype == LFE_F64) k_expand_dummies<double><<<blocks, 256, 0, s>>>(codes, base, n, sp);
+    else k_expand_dummies<uint8_t><<<blocks, 256, 0, s>>>(codes, nullptr, n, sp);
+    KERNEL_CHECK();
+    h->n_launches += 1;
+  }
+}

@@ -372,6 +372,21 @@ class Engine:
         capi.check(self.lib.lfe_allreduce_f64(self.h, self._p(t), t.numel(), self.stream))
         return t
 
+    def expand_dummies(self, codes: torch.Tensor, levels: list[int], base: torch.Tensor | None = None,
+                       as_uint8: bool = False) -> list[torch.Tensor]:
+        """lfe_expand_dummies: the dummy columns (codes == level) [* base] of all ``levels`` in one pass."""
+        self._check_dev(codes, base)
+        n, J = codes.numel(), len(levels)
+        if codes.dtype != torch.int32 or (base is not None and (base.dtype != torch.float64 or base.numel() != n)):
+            raise ValueError("expand_dummies: int32 codes and a float64 base of the same length")
+        dt = torch.uint8 if (as_uint8 and base is None) else torch.float64
+        out = [self.empty(n, dt) for _ in range(J)]
+        if J:
+            capi.check(self.lib.lfe_expand_dummies(self.h, self._p(codes), n, capi.i32_array(levels), J, self._p(base),
+                                                   _TORCH_TO_LFE[dt], capi.ptr_array([t.data_ptr() for t in out]),
+                                                   self.stream))
+        return out
+
     def shard_plan(self, codes: torch.Tensor, n_groups: int):
         """lfe_shard_plan: balanced code-range cuts of the shard key + this rank's send order.
         -> dict(cuts, send_counts, recv_counts, order)"""
