@@ -65,6 +65,16 @@ const char* lfe_last_error(void);
 int lfe_create(int device, lfe_handle* out);
 int lfe_destroy(lfe_handle h);
 
+/* Tuning knobs of a handle (all optional).
+ * LFE_OPT_COLUMNS_HINT: number of columns C the next demean plans will run with (y + regressors); with it,
+ *   lfe_demean_plan_create can order the entry lists in L2-sized blocks of the highest-cardinality FE when that FE's
+ *   [G x C] table does not fit the L2 (0 = unknown: no blocking).
+ * LFE_OPT_L2_BLOCK_BYTES: bytes of one such table slice (default 48 MB; the B200 L2 is 126 MB over two partitions).
+ * LFE_OPT_DETERMINISTIC: 1 = run-to-run bit-identical results (fixed-order reductions instead of floating-point
+ *   atomics) on the paths that support it, see lfe_demean.                                                  */
+enum { LFE_OPT_COLUMNS_HINT = 1, LFE_OPT_L2_BLOCK_BYTES = 2, LFE_OPT_DETERMINISTIC = 3 };
+int lfe_set_option(lfe_handle h, int option, int64_t value);
+
 /* Per-phase CUDA-event timers (ms, accumulated since the last reset); enabling costs two
  * cudaEventRecord per phase.  lfe_get_timers synchronises the recorded events.
  * slots: 0 factorize, 1 counts/singletons, 2 compact, 3 sort, 4 gather, 5 demean-setup (CSR + S0),

@@ -21,10 +21,11 @@ N_TIMERS = 16
 TIMER_NAMES = ["factorize", "counts_singletons", "compact", "sort", "gather", "demean_setup", "demean_sweeps",
                "demean_check", "demean_apply", "gram", "solve", "resid_vcov", "compress", "collectives", "repartition", "_15"]
 ERR_CAPACITY = -3
+OPT_COLUMNS_HINT, OPT_L2_BLOCK_BYTES, OPT_DETERMINISTIC = 1, 2, 3
 
 EXPORTS = [
     "lfe_version", "lfe_last_error", "lfe_create", "lfe_destroy", "lfe_set_profiling", "lfe_reset_timers",
-    "lfe_get_timers", "lfe_get_counters", "lfe_factorize", "lfe_factorize_counts", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
+    "lfe_get_timers", "lfe_get_counters", "lfe_set_option", "lfe_factorize", "lfe_factorize_counts", "lfe_group_counts", "lfe_singleton_mask", "lfe_compact",
     "lfe_sort_rows", "lfe_gather", "lfe_demean", "lfe_demean_plan_create", "lfe_demean_plan_run",
     "lfe_demean_plan_destroy", "lfe_demean_plan_fit", "lfe_gram", "lfe_solve_spd", "lfe_resid_vcov", "lfe_compress", "lfe_yoco_vcov",
     "lfe_compress_merge", "lfe_key_ranges", "lfe_comm_unique_id", "lfe_comm_init", "lfe_comm_destroy", "lfe_comm_set_active",
@@ -59,6 +60,7 @@ def load_library() -> C.CDLL:
     lib.lfe_create.argtypes = [i32, P(vp)]
     lib.lfe_destroy.argtypes = [vp]
     lib.lfe_set_profiling.argtypes = [vp, i32]
+    lib.lfe_set_option.argtypes = [vp, i32, i64]
     lib.lfe_reset_timers.argtypes = [vp]
     lib.lfe_get_timers.argtypes = [vp, P(dbl)]
     lib.lfe_get_counters.argtypes = [vp, P(i64)]

@@ -356,10 +356,13 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
             cols, w = f_out[: k + 1], (f_out[k + 1] if w is not None else None)
             new_of = {id(o): n_ for o, n_ in zip(codes + extra, i_out)}
             codes, cl_codes = i_out[:F], [new_of[id(c)] for c in cl_codes]
-            plan = eng.demean_plan(codes, Gs, w, local_fe)
+            plan = eng.demean_plan(codes, Gs, w, local_fe, columns_hint=k + 1)
         else:
             # rows are never permuted: the plan sorts only the int32 code columns (one entry list per FE)
-            plan = eng.demean_plan(codes, Gs, w, local_fe, counts)
+            lazy_ = getattr(get_columns, "lazy", None)
+            per_column = lazy_ is not None and strategy == "alt_proj" and lazy_["pending"]()
+            hint = 1 if per_column else (len(lazy_["x"]) + 1 if lazy_ is not None else None)
+            plan = eng.demean_plan(codes, Gs, w, local_fe, counts, columns_hint=hint)
             cols = None
         del keep, counts
         lazy = getattr(get_columns, "lazy", None)
@@ -595,7 +598,25 @@ def _solve_compressed(eng: Engine, comp, xk, kc, cl_idx, x_cols, fe_keys, k, F, 
                           f"fixed point in {sweeps} sweeps (poorly connected fixed effects); coefficients and standard "
                           "errors may be inaccurate", RuntimeWarning, stacklevel=3)
         gram = eng.gram(cols[1:] + [cols[0]], nn, add_intercept=False)
-        beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
+        try:
+            beta, B, _ = eng.solve_spd(gram[:k, :k].contiguous(), gram[:k, k].contiguous())
+        except capi.LfeError as e:
+            if "singular" not in str(e):
+                raise
+            # Singular design (e.g. a dummy that is never 1): the reference's Cholesky raises and it falls back to
+            # the minimum-norm solution, np.linalg.lstsq + np.linalg.pinv of the normal equations
+            # (compress.py:742-745).  Same two LAPACK calls here, on the k x k FWL system (k <= 512, host): for
+            # all-zero / duplicated regressors this is the x-block of the reference's full-system answer; a
+            # regressor collinear with the FE dummies gets coefficient 0 here (the reference spreads it over the
+            # dummies it then discards).
+            warnings.warn("strategy='compress': the regressors are collinear after absorbing the fixed effects; "
+                          "returning the minimum-norm solution (as the reference's lstsq/pinv fallback)",
+                          RuntimeWarning, stacklevel=3)
+            g_host = gram.cpu().numpy()
+            beta_h = np.linalg.lstsq(g_host[:k, :k], g_host[:k, k], rcond=None)[0]
+            B_h = np.linalg.pinv(g_host[:k, :k])
+            beta = torch.from_numpy(np.ascontiguousarray(beta_h)).to(eng.device)
+            B = torch.from_numpy(np.ascontiguousarray(B_h)).to(eng.device)
         p = 1 + k + sum(g - 1 for g in fe_G)
         df_resid = n_obs - p
         out = eng.yoco_vcov(cols, beta, B, nn, sy, syy, vkind, [kout[i] for i in cl_idx], [kc[i][1] for i in cl_idx],

@@ -243,6 +243,20 @@ int lfe_destroy(lfe_handle h) {
   LFE_API_END
 }
 
+int lfe_set_option(lfe_handle h, int option, int64_t value) {
+  LFE_API_BEGIN
+  LFE_REQUIRE(h != nullptr, "lfe_set_option: handle is NULL");
+  switch (option) {
+    case LFE_OPT_COLUMNS_HINT: h->opt_columns_hint = (int)(value < 0 ? 0 : value); break;
+    case LFE_OPT_L2_BLOCK_BYTES:
+      LFE_REQUIRE(value >= (1 << 20), "lfe_set_option: L2 block must be >= 1 MB");
+      h->opt_l2_block_bytes = value;
+      break;
+    case LFE_OPT_DETERMINISTIC: h->opt_deterministic = value != 0; break;
+    default: LFE_THROW(LFE_ERR_ARG, "lfe_set_option: unknown option %d", option);
+  }
+  LFE_API_END
+}
 int lfe_set_profiling(lfe_handle h, int enabled) {
   LFE_API_BEGIN
   h->profiling = enabled != 0;

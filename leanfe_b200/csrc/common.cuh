@@ -83,6 +83,10 @@ struct lfe_ctx {
   } last_counts;
   int64_t last_counts_G = -1;
   const void* last_counts_codes = nullptr;
+  // lfe_set_option
+  int opt_columns_hint = 0;                 // columns per demean run (0 = unknown): sizes the L2 blocks of the entry lists
+  int64_t opt_l2_block_bytes = 48ll << 20;  // a table slice this large is expected to stay L2-resident while it is gathered
+  int opt_deterministic = 0;
 };
 
 // RAII phase timer: records a CUDA-event pair on the stream when profiling is on.

@@ -51,6 +51,36 @@ __global__ void k_split_gram(const double* __restrict__ G, int p, double* __rest
   for (int i = threadIdx.x; i < p * p; i += blockDim.x) A[i] = G[(i / p) * P + (i % p)];
   for (int i = threadIdx.x; i < p; i += blockDim.x) b[i] = G[i * P + p];
 }
+// IID standard errors from the Gram alone.  G is (p+1) x (p+1) over [1, x.., y]; beta (p) solves G[:p,:p] beta = G[:p,p].
+// stats = {rss, tss, rss, 0}; ok = 0 when rss is too small a difference of its terms to be trusted.
+__global__ void __launch_bounds__(256) k_iid_from_gram(const double* __restrict__ G, const double* __restrict__ beta,
+                                                       const double* __restrict__ B, int p, double n_obs, double df,
+                                                       double* __restrict__ se, double* __restrict__ vcov,
+                                                       double* __restrict__ stats, int* __restrict__ ok) {
+  __shared__ double rss_s;
+  const int P = p + 1, k = p - 1;
+  if (threadIdx.x == 0) {
+    const double yy = G[p * P + p];
+    double bxy = 0.0;
+    for (int a = 0; a < p; ++a) bxy += beta[a] * G[a * P + p];
+    const double rss = yy - bxy;
+    const double sy = G[0 * P + p];
+    stats[0] = rss;
+    stats[1] = yy - sy * sy / n_obs;
+    stats[2] = rss;
+    stats[3] = 0.0;
+    rss_s = rss;
+    *ok = (rss > 1e-6 * yy && rss > 0.0) ? 1 : 0;
+  }
+  __syncthreads();
+  const double sc = rss_s / df;
+  for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+    const double v = sc * B[idx];
+    if (vcov) vcov[idx] = v;
+    if (idx / k == idx % k) se[idx / k] = sqrt(fmax(v, 0.0));
+  }
+}
+
 // B = Ainv[1:, 1:]
 __global__ void k_drop_intercept(const double* __restrict__ Ainv, int p, double* __restrict__ B) {
   const int k = p - 1;
@@ -944,10 +974,37 @@ struct lfe_plan {
   bool weighted = false;
   int local_fe = -1;
   int big = 0;   // highest-cardinality FE: its entry list was built first
+  int block_bits = 0;   // > 0: the other FEs' lists are ordered in L2 blocks of the big FE's codes (l2_block_bits)
   const int32_t* codes[LFE_MAX_FE] = {nullptr};
   const double* weights = nullptr;
   std::vector<FEState> st;
 };
+
+// L2 blocking of the entry lists.  A projection on a non-big FE gathers rows of the BIG FE's [G x C] table in
+// ascending order inside every group; when that table outgrows the L2 (c5: 4M units x 12 columns = 384 MB, c3: 10M
+// workers x 3 = 240 MB) the sparse ascending walk re-fetches it from HBM for every group (ncu: the c5 time
+// projection moved 77 GB per sweep for 1.6 GB of entry words).  Ordering the list by (block of the big code, own
+// code, big code) instead -- one more stable radix pass on the block bits -- makes each table slice of
+// opt_l2_block_bytes L2-resident while all entries that gather from it are processed; a group is then split into
+// at most 2^bits runs (a few more RED.ADD.F64 per group).  Returns the number of block bits (0 = no blocking).
+static int l2_block_bits(const lfe_ctx* h, int64_t G_big, int F) {
+  if (h->opt_columns_hint <= 0 || F < 2) return 0;
+  const int C = h->opt_columns_hint;
+  const int64_t row_bytes = (int64_t)((C >= 5 && (C & 1)) ? C + 1 : C) * 8;
+  if (G_big * row_bytes <= h->opt_l2_block_bytes + h->opt_l2_block_bytes / 2) return 0;
+  int64_t block_codes = 1;
+  while (block_codes * 2 * row_bytes <= h->opt_l2_block_bytes) block_codes *= 2;
+  const int bb = bits_for((uint64_t)(G_big - 1)), lb = bits_for((uint64_t)(block_codes - 1));
+  const int bits = bb - lb;
+  return bits < 0 ? 0 : (bits > 8 ? 8 : bits);
+}
+
+// out[i] = code[i] >> shift
+__global__ void __launch_bounds__(256) k_block_of(const int32_t* __restrict__ code, int64_t n, int shift,
+                                                  uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    __stcs(out + i, (uint32_t)__ldcs(code + i) >> shift);
+}
 
 lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int64_t* n_groups, int F, int64_t n,
                              const double* weights, int local_fe, const int32_t* const* counts_in, cudaStream_t s) {
@@ -995,6 +1052,14 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
       prim_sort_keys_u32(h, (const uint32_t*)words.p, n, bs, bb, (uint32_t*)B.key_buf.p, s);
       M.key_buf.alloc(n, s);
       prim_sort_keys_u32(h, (const uint32_t*)B.key_buf.p, n, 0, bs, (uint32_t*)M.key_buf.p, s);
+      const int blk_bits = l2_block_bits(h, B.G, F);
+      if (blk_bits > 0) {
+        // (small, big) order -> (block of big, small, big): one more stable pass on the top bits of the big code
+        DevBuf<int32_t> blocked(n, s);
+        prim_sort_keys_u32(h, (const uint32_t*)M.key_buf.p, n, bs + bb - blk_bits, blk_bits, (uint32_t*)blocked.p, s);
+        M.key_buf = std::move(blocked);
+      }
+      plan->block_bits = blk_bits;
       B.key = B.key_buf; B.packed = true; B.pk = PackSpec{bs, 0, bmask, smask};
       M.key = M.key_buf; M.packed = true; M.pk = PackSpec{0, bs, smask, bmask};
       B.oth[sm] = nullptr; M.oth[big] = nullptr;
@@ -1032,6 +1097,23 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
           prim_gather_i32(codes[j], base_perm, n, kin, s);
           prim_sort_pairs_u32(h, (const uint32_t*)kin.p, base_perm, n, kb, (uint32_t*)S.key_buf.p, S.perm, s);
           h->n_launches += 1;
+          // (narrow rows -- C <= 4 -- waste little of a 32-byte sector and their gathers are bound by the L1TEX
+          // pipe, not by HBM: c3 gained nothing; an FE small enough for k_proj_tiny never uses its own list)
+          const bool tiny_j = S.G * (h->opt_columns_hint < PJ_MAXNC ? h->opt_columns_hint : PJ_MAXNC) <= PT_MAX_BINS;
+          const int blk_bits = (st[big].identity || h->opt_columns_hint < 5 || tiny_j) ? 0 : l2_block_bits(h, st[big].G, F);
+          if (blk_bits > 0) {
+            // (own, big) order -> (block of big, own, big): stable pass on the block index of the big code
+            const int shift = bits_for((uint64_t)(st[big].G - 1)) - blk_bits;
+            DevBuf<uint32_t> bk(n, s), bk_sorted(n, s), perm2(n, s);
+            prim_gather_i32(codes[big], S.perm, n, kin, s);
+            k_block_of<<<launch_blocks(h, ceil_div64(n, 256 * 4), 8), 256, 0, s>>>(kin, n, shift, bk);
+            KERNEL_CHECK();
+            prim_sort_pairs_u32(h, bk, S.perm, n, blk_bits, bk_sorted, perm2, s);
+            S.perm = std::move(perm2);
+            prim_gather_i32(codes[j], S.perm, n, S.key_buf, s);
+            h->n_launches += 3;
+            plan->block_bits = blk_bits;
+          }
         }
         S.key = S.key_buf;
         for (int k = 0; k < F; ++k) {
@@ -1199,9 +1281,28 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
   double max_mean = 0.0;
 
   // accumulate the projection sums of FE j over all column batches (+ cross-rank sum for non-local FEs)
+  // LFE_TRACE_PROJ=1: per-projection device times (CUDA events around every projection, printed when the run ends)
+  static const bool trace_proj = getenv("LFE_TRACE_PROJ") != nullptr;
+  struct ProjTrace { int j; cudaEvent_t a, b; };
+  std::vector<ProjTrace> trace;
+  struct TraceDump {
+    std::vector<ProjTrace>& tr;
+    ~TraceDump() {
+      for (auto& e : tr) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess)
+          fprintf(stderr, "lfe trace: projection on FE %d: %.4f ms\n", e.j, ms);
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+      }
+    }
+  } trace_dump{trace};
   auto project = [&](int j) {
     FEState& S = st[j];
     if (F == 1) return;
+    ProjTrace tr{j, nullptr, nullptr};
+    if (trace_proj) { cudaEventCreate(&tr.a); cudaEventCreate(&tr.b); cudaEventRecord(tr.a, s); }
+    struct Rec { ProjTrace& t; std::vector<ProjTrace>& v; cudaStream_t s; bool on;
+                 ~Rec() { if (on) { cudaEventRecord(t.b, s); v.push_back(t); } } } rec{tr, trace, s, trace_proj};
     ProjOthers o = others_of(j, false);
     // a very small FE is projected over the big FE's entry list with thread-private bins (k_proj_tiny)
     const int big = plan->big;
@@ -1353,6 +1454,23 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
     k_drop_intercept<<<1, 256, 0, s>>>(Ainv, p, B);
     KERNEL_CHECK();
     h->n_launches += 2;
+    if ((tail->vcov_kind & 0xff) == LFE_VCOV_IID && !weighted && p > 1) {
+      // IID needs only rss (std_errors.py:183-210): with the normal equations solved, rss = y~'y~ - beta'X~'y~ and
+      // tss = y~'y~ - (1'y~)^2 / n are already in the (all-reduced) Gram -- no second pass over the rows.  Guarded:
+      // when the fit is so tight that the difference cancels (rss < 1e-6 y~'y~) the explicit residual pass runs.
+      PhaseTimer tv(h, s, 11);
+      DevBuf<int> ok(1, s);
+      DevBuf<double> stats_local(4, s);
+      double* stats = tail->stats_out ? tail->stats_out : stats_local.p;
+      k_iid_from_gram<<<1, 256, 0, s>>>(gram, tail->beta_full_out, B, p, (double)tail->n_obs, (double)tail->df_resid,
+                                        tail->se_out, tail->vcov_out, stats, ok);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      int hok = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&hok, ok.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (hok) return;
+    }
     resid_vcov_fused_impl(h, in, C, n, T, Cp, tab_smem, tail->beta_full_out, B, tail->vcov_kind, tail->cl_codes,
                           tail->n_cl_groups, weights, tail->ssc, tail->n_obs, tail->df_resid, tail->se_out,
                           tail->vcov_out, tail->stats_out, tail->n_clusters_out, s);

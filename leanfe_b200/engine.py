@@ -111,6 +111,10 @@ class Engine:
             if t is not None and (not t.is_cuda or not t.is_contiguous()):
                 raise ValueError("expected contiguous CUDA tensors")
 
+    def set_option(self, option: int, value: int):
+        """lfe_set_option (capi.OPT_*)."""
+        capi.check(self.lib.lfe_set_option(self.h, int(option), int(value)))
+
     # -- profiling -----------------------------------------------------------------------------
     def set_profiling(self, on: bool):
         capi.check(self.lib.lfe_set_profiling(self.h, 1 if on else 0))
@@ -240,10 +244,12 @@ class Engine:
         return int(it.value), float(mm.value), bool(cv.value)
 
     def demean_plan(self, codes: list[torch.Tensor], n_groups: list[int], weights: torch.Tensor | None = None,
-                    local_fe: int = -1, counts=None) -> "DemeanPlan":
+                    local_fe: int = -1, counts=None, columns_hint: int | None = None) -> "DemeanPlan":
         """Column-independent part of lfe_demean (entry lists, group sizes); see ``DemeanPlan.run``.
-        ``counts`` (optional) = per-FE int32 group sizes from ``group_counts`` (saves one pass per FE)."""
-        return DemeanPlan(self, codes, n_groups, weights, local_fe, counts)
+        ``counts`` (optional) = per-FE int32 group sizes from ``group_counts`` (saves one pass per FE);
+        ``columns_hint`` = columns the plan will be run with at once (lets the library block the entry lists for
+        the L2 when the biggest FE table does not fit it)."""
+        return DemeanPlan(self, codes, n_groups, weights, local_fe, counts, columns_hint)
 
     # -- (4) gram / solve ---------------------------------------------------------------------
     def gram(self, cols: list[torch.Tensor], weights: torch.Tensor | None = None, add_intercept: bool = True):
@@ -477,7 +483,7 @@ class _Replicated:
 class DemeanPlan:
     """lfe_demean_plan_*: built from the code columns only, runnable on any number of column sets."""
 
-    def __init__(self, eng: Engine, codes, n_groups, weights, local_fe, counts=None):
+    def __init__(self, eng: Engine, codes, n_groups, weights, local_fe, counts=None, columns_hint=None):
         eng._check_dev(*codes, weights)
         self.eng, self.codes, self.weights, self.n_groups = eng, list(codes), weights, list(n_groups)   # keep alive
         self.n = codes[0].numel()
@@ -485,6 +491,7 @@ class DemeanPlan:
             if t.dtype != torch.int32 or t.numel() != self.n:
                 raise ValueError("codes must be int32 tensors of equal length")
         p = C.c_void_p()
+        eng.set_option(capi.OPT_COLUMNS_HINT, int(columns_hint or 0))
         capi.check(eng.lib.lfe_demean_plan_create(eng.h, capi.ptr_array([t.data_ptr() for t in codes]),
                                                   capi.i64_array(n_groups), len(codes), self.n, eng._p(weights),
                                                   int(local_fe),

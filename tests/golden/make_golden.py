@@ -183,6 +183,22 @@ def main():
                 out[f"comp_key_{nm}"] = c["keys"][j]
             out["comp_n"], out["comp_sum_y"], out["comp_sum_y_sq"] = c["n"], c["sum_y"], c["sum_y_sq"]
     np.savez_compressed(os.path.join(HERE, "yoco.npz"), **out)
+
+    # ---- YOCO on a SINGULAR design: a regressor that is identically zero makes the reference's Cholesky raise, so
+    # its lstsq / pinv fallback (compress.py:742-745) produces the numbers below --------------------------------
+    d = panel_yoco()
+    d["x0"] = np.zeros_like(d["y"])
+    out = dict(d)
+    for vc, ssc, cl in (("iid", True, None), ("HC1", True, None), ("cluster", True, ["grp"])):
+        r = O.leanfe_oracle({k: v for k, v in d.items() if k != "x0"}, formula="y ~ xd + x2 | grp + per", strategy="compress",
+                            vcov=vc, cluster_cols=cl, ssc=ssc, return_internals=True)
+        comp = O.compress(d["y"], [d["xd"], d["x0"], d["x2"], d["grp"], d["per"]])
+        comp["n_obs"] = len(d["y"])
+        rr = RL.reference_yoco(ref, comp, ["xd", "x0", "x2"], ["grp", "per"], vc, ssc, cl)
+        tag = f"{vc.lower()}_ssc{int(ssc)}" + ("_" + "_".join(cl) if cl else "")
+        out[f"ref_beta_{tag}"], out[f"ref_se_{tag}"] = rr["beta"], rr["se"]
+        out[f"ref_df_resid_{tag}"], out[f"ref_rss_{tag}"] = rr["df_resid"], rr["rss"]
+    np.savez_compressed(os.path.join(HERE, "yoco_singular.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

@@ -350,3 +350,23 @@ def test_pageable_ingest_ring_is_bit_exact_for_every_source_kind():
         r = leanfe(d, formula="y ~ x | f + g", vcov="cluster", cluster_cols=["f"])
         assert r.coefs["x"] == pytest.approx(base.coefs["x"], rel=1e-12)
         assert r.std_errors["x"] == pytest.approx(base.std_errors["x"], rel=1e-12)
+
+
+@pytest.mark.parametrize("vcov,cl", [("iid", None), ("HC1", None), ("cluster", ["grp"])])
+def test_yoco_singular_design_takes_the_references_min_norm_fallback(golden_dir, vcov, cl):
+    """A regressor that is identically zero makes the normal equations singular: the reference's Cholesky raises and
+    it returns np.linalg.lstsq / pinv numbers (compress.py:742-745).  Golden = the reference's own solve_wls +
+    compute_se_compress on that design (tests/golden/make_golden.py)."""
+    from leanfe_b200 import leanfe
+    g = _golden(golden_dir, "yoco_singular.npz")
+    d = {k: g[k] for k in ("y", "xd", "x0", "x2", "grp", "per", "st")}
+    tag = f"{vcov.lower()}_ssc1" + ("_" + "_".join(cl) if cl else "")
+    with pytest.warns(RuntimeWarning, match="collinear"):
+        res = leanfe(d, formula="y ~ xd + x0 + x2 | grp + per", strategy="compress", vcov=vcov, cluster_cols=cl)
+    eb, es = g[f"ref_beta_{tag}"], g[f"ref_se_{tag}"]
+    b, s = np.array(list(res.coefs.values())), np.array(list(res.std_errors.values()))
+    for j in (0, 2):
+        assert abs(b[j] - eb[j]) / abs(eb[j]) < RTOL_BETA and abs(s[j] - es[j]) / es[j] < RTOL_SE
+    assert abs(b[1]) < 1e-10 and abs(eb[1]) < 1e-10 and s[1] < 1e-12 and es[1] < 1e-12       # the dead column
+    assert res.df_resid == int(g[f"ref_df_resid_{tag}"])
+    assert res.rss == pytest.approx(float(g[f"ref_rss_{tag}"]), rel=1e-9)

@@ -676,3 +676,28 @@ def test_plan_fit_matches_run_gram_solve_vcov(eng, C, Gs, weighted, n, offset):
     # the raw columns were only read
     np.testing.assert_array_equal(raw[0].cpu().numpy(), y)
     plan.close()
+
+
+@pytest.mark.parametrize("Gs,C,weighted", [((300_000, 400), 6, False), ((200_000, 3_000, 25), 6, False),
+                                            ((150_000, 2_000), 4, True), ((70_000, 60_000), 11, False)])
+def test_demean_l2_blocked_entry_lists_match_oracle(eng, Gs, C, weighted):
+    """LFE_OPT_COLUMNS_HINT + a small LFE_OPT_L2_BLOCK_BYTES force the (block of the big code, own code, big code)
+    list order: groups are split into several runs, the sums must not change."""
+    from leanfe_b200 import _capi as capi
+    rng = np.random.default_rng(sum(Gs) + C)
+    n = 400_000
+    fe = [rng.integers(0, g, n).astype(np.int32) for g in Gs]
+    cols = [rng.normal(size=n) + 0.2 * rng.normal(size=Gs[0])[fe[0]] for _ in range(C)]
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    order = sorted(range(len(Gs)), key=lambda j: Gs[j])
+    exp, _, _ = O.alt_proj(cols, fe, order, 0.0, 4, w)                           # exactly 4 sweeps
+    eng.set_option(capi.OPT_L2_BLOCK_BYTES, 1 << 20)
+    try:
+        plan = eng.demean_plan([dev(f) for f in fe], list(Gs), dev(w) if weighted else None, columns_hint=C)
+        got = [dev(c) for c in cols]
+        plan.run(got, order, 0.0, 4, 3)
+        plan.close()
+    finally:
+        eng.set_option(capi.OPT_L2_BLOCK_BYTES, 48 << 20)
+    for a, b in zip(got, exp):
+        np.testing.assert_allclose(a.cpu().numpy(), b, rtol=0, atol=2e-12)
