@@ -11,6 +11,7 @@ actually needs it.
 from __future__ import annotations
 
 import contextlib
+import os
 import time
 import warnings
 
@@ -35,7 +36,7 @@ _VCOV = {"iid": capi.VCOV_IID, "hc1": capi.VCOV_HC1, "cluster": capi.VCOV_CLUSTE
 
 def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strategy="auto", weights=None,
            demean_tol=1e-6, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None,
-           backend="polars", con=None, device=None, profile=False, local_fe=None) -> LeanFEResult:
+           backend="polars", con=None, device=None, profile=False, local_fe=None, deterministic=None) -> LeanFEResult:
     """Fast fixed-effects regression; drop-in for ``leanfe.leanfe`` with the compute on a B200.
 
     ``backend`` accepts "polars" (the backend this package replaces), "b200" or "cuda"; "duckdb" is a
@@ -47,7 +48,7 @@ def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strateg
         return leanfe_b200(data=data, y_col=y_col, x_cols=x_cols, fe_cols=fe_cols, formula=formula,
                            strategy=strategy, weights=weights, demean_tol=demean_tol, max_iter=max_iter, vcov=vcov,
                            cluster_cols=cluster_cols, ssc=ssc, sample_frac=sample_frac, device=device,
-                           profile=profile, local_fe=local_fe)
+                           profile=profile, local_fe=local_fe, deterministic=deterministic)
     if backend == "duckdb":
         raise ValueError("backend='duckdb' is not provided by leanfe_b200 (out of scope: it replaces the Polars "
                          "backend's compute); use backend='polars'")
@@ -56,7 +57,7 @@ def leanfe(data=None, y_col=None, x_cols=None, fe_cols=[], formula=None, strateg
 
 def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, formula=None, strategy="auto",
                 weights=None, max_iter=50, vcov="iid", cluster_cols=None, ssc=True, sample_frac=None, device=None,
-                profile=False, local_fe=None) -> LeanFEResult:
+                profile=False, local_fe=None, deterministic=None) -> LeanFEResult:
     """Counterpart of ``leanfe_polars`` (polars_impl.py:287-301) on the device.
 
     Multi-GPU (one process per GPU, ``Engine.comm_init_from_torch()`` called): ``data`` holds THIS rank's
@@ -105,6 +106,15 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         needed.append(weights)
 
     eng = get_engine(device)
+    if deterministic is None:
+        deterministic = os.environ.get("LFE_DETERMINISTIC", "0") not in ("", "0")
+    if deterministic:
+        if eng.world > 1:
+            raise NotImplementedError("deterministic=True is single-GPU only")
+        if strategy in ("auto", "compress"):
+            raise NotImplementedError("deterministic=True covers the FWL strategies: pass strategy='alt_proj', "
+                                      "'demean' or 'ols' (the YOCO group-by sums with atomics)")
+    eng.set_option(capi.OPT_DETERMINISTIC, 1 if deterministic else 0)
     if profile:
         eng.set_profiling(True)
         eng.reset_timers()
@@ -309,7 +319,8 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
             cl_local = bool(dist and cluster_cols and len(cluster_cols) == 1 and cluster_cols[0] == local_fe)
             w_early = num(weights) if weights is not None else None
             res = _fit_fwl(eng, strategy, get_columns, fe_keys, fe_cols, cl_keys, w_early, vcov, vkind, ssc, demean_tol,
-                           max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None, fe_card_order)
+                           max_iter, formula, est_ratio, lf, cl_local, iv_state if instruments else None, fe_card_order,
+                       deterministic)
         if profile:
             torch.cuda.synchronize(eng.device)
             res.timings = dict(eng.timers(), wall_ms=(time.perf_counter() - t_start) * 1e3, **eng.counters())
@@ -321,7 +332,7 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
 
 # ------------------------------------------------------------------------------------------------
 def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, vcov, vkind, ssc, tol, max_iter,
-             formula, est_ratio, local_fe=-1, cl_local=False, iv=None, fe_card=None) -> LeanFEResult:
+             formula, est_ratio, local_fe=-1, cl_local=False, iv=None, fe_card=None, deterministic=False) -> LeanFEResult:
     """'alt_proj' (polars_impl.py:468-537), 'demean' (:424-465) and 'ols' (:541-547) + _run_regression.
 
     ``get_columns()`` -> (y, X, names, w) is called as late as possible: the singleton test and the demean plan
@@ -395,6 +406,7 @@ def _fit_fwl(eng: Engine, strategy, get_columns, fe_keys, fe_cols, cl_keys, w, v
                 raw = cols
             kind = vkind & 0xFF
             if (iv is None and len(raw) <= plan.FIT_MAX_COLS and (kind != capi.VCOV_CLUSTER or len(cl_codes) == 1)
+                    and not (deterministic and kind == capi.VCOV_CLUSTER)
                     and all(t.dtype == torch.float64 and t.is_contiguous() for t in raw)):
                 # the usual fit: one library call, the demeaned columns are formed in registers and never written
                 # (lfe_demean_plan_fit); df_resid needs only fe_dims, known since the singleton pass

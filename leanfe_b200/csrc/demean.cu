@@ -438,6 +438,72 @@ __global__ void __launch_bounds__(PJ_T) k_segsum(const int32_t* __restrict__ key
   }
 }
 
+// ---- deterministic mode (LFE_OPT_DETERMINISTIC): group sums in a FIXED order, no floating-point atomics -----------
+// One warp owns one group of the FE-sorted entry list, entries [off[g], off[g+1]): lane l adds entries l, l + 32, ...
+// sequentially, then a fixed xor-shuffle tree combines the 32 partials and lane 0 STORES the sum.  Every bit of the
+// result is a function of the data and the list order alone, so two runs agree exactly.  (Slower than the
+// run-merging kernels for long groups -- one warp walks a whole group -- and meant for tests and audits.)
+// acc[g][acc_col0 + c] = sum_e w_e sum_k alpha_k[oth_k[e]][col0 + c]
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_det_proj(const uint32_t* __restrict__ off, int64_t G, ProjOthers oth,
+                                                  const double* __restrict__ w, int ldc, int col0,
+                                                  double* __restrict__ acc, int ld_acc, int acc_col0) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < G; g += nwarp) {
+    double sum[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = 0.0;
+    const uint32_t e1 = off[g + 1];
+    for (uint32_t e = off[g] + lane; e < e1; e += 32) {
+      double v[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[c] = 0.0;
+      for (int o = 0; o < oth.n; ++o) {
+        const double* row = oth.alpha[o] + (size_t)oth.code[o][e] * ldc + col0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] += row[c];
+      }
+      const double we = WEIGHTED ? w[e] : 1.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sum[c] += WEIGHTED ? v[c] * we : v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = warp_sum(sum[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[(size_t)g * ld_acc + acc_col0 + c] = sum[c];
+    }
+  }
+}
+// acc[g][acc_col0 + c] = sum_e w[row_e] col_c[row_e],  row_e = perm ? perm[e] : e
+template <int NC, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_det_s0(const uint32_t* __restrict__ off, int64_t G,
+                                                const uint32_t* __restrict__ perm, ColPtrs cols,
+                                                const double* __restrict__ w_rows, double* __restrict__ acc, int ld_acc,
+                                                int acc_col0) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < G; g += nwarp) {
+    double sum[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = 0.0;
+    const uint32_t e1 = off[g + 1];
+    for (uint32_t e = off[g] + lane; e < e1; e += 32) {
+      const size_t row = perm ? perm[e] : e;
+      const double we = WEIGHTED ? w_rows[row] : 1.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sum[c] += WEIGHTED ? cols.col[c][row] * we : cols.col[c][row];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = warp_sum(sum[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[(size_t)g * ld_acc + acc_col0 + c] = sum[c];
+    }
+  }
+}
+
 // alpha <- (S0 - acc) / nsum ; acc <- 0
 // Low-cardinality FE: per-CTA privatised fp64 bins in shared memory (G*NC*8 bytes), rows in their original
 // order with coalesced column loads; the CTA's bins are flushed with one RED.ADD.F64 per non-zero bin.
@@ -728,6 +794,7 @@ struct FEState {
   DevBuf<double> w_buf;
   const double* w = nullptr;
   DevBuf<double> alpha, S0, acc, nsum, cnt_buf, S0u_buf, acc_chk;
+  DevBuf<uint32_t> off;   // deterministic mode: CSR offsets of the groups in the sorted entry list (G + 1)
   const double* cnt = nullptr;  // unweighted counts
   const double* S0u = nullptr;  // unweighted y sums
   int ld_s0u = 1;
@@ -965,6 +1032,38 @@ static void launch_apply(lfe_ctx* h, int nc, const MutColPtrs& cols, const Apply
   h->n_launches += 1;
 }
 
+template <bool WEIGHTED>
+static void launch_det_proj(lfe_ctx* h, int nc, const FEState& S, const ProjOthers& oth, int ldc, int col0, double* acc,
+                            int ld_acc, int acc_col0, cudaStream_t s) {
+  const int blocks = launch_blocks(h, ceil_div64(S.G, 8), 8);
+#define DP_CASE(NC_) \
+  case NC_: k_det_proj<NC_, WEIGHTED><<<blocks, 256, 0, s>>>(S.off, S.G, oth, S.w, ldc, col0, acc, ld_acc, acc_col0); break;
+  switch (nc) {
+    DP_CASE(1) DP_CASE(2) DP_CASE(3) DP_CASE(4) DP_CASE(5) DP_CASE(6) DP_CASE(7) DP_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_det_proj: nc=%d", nc);
+  }
+#undef DP_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+  h->n_sweep_launches += 1;
+}
+// w_rows: weights in ROW order (nullable)
+template <bool WEIGHTED>
+static void launch_det_s0(lfe_ctx* h, int nc, const FEState& S, const ColPtrs& cols, const double* w_rows, double* acc,
+                          int ld_acc, int acc_col0, cudaStream_t s) {
+  const int blocks = launch_blocks(h, ceil_div64(S.G, 8), 8);
+  const uint32_t* perm = S.identity ? nullptr : S.perm.p;
+#define DS_CASE(NC_) \
+  case NC_: k_det_s0<NC_, WEIGHTED><<<blocks, 256, 0, s>>>(S.off, S.G, perm, cols, w_rows, acc, ld_acc, acc_col0); break;
+  switch (nc) {
+    DS_CASE(1) DS_CASE(2) DS_CASE(3) DS_CASE(4) DS_CASE(5) DS_CASE(6) DS_CASE(7) DS_CASE(8)
+    default: LFE_THROW(LFE_ERR_ARG, "launch_det_s0: nc=%d", nc);
+  }
+#undef DS_CASE
+  KERNEL_CHECK();
+  h->n_launches += 1;
+}
+
 // The column-independent part of a fit: entry lists and group sizes.  Built from the code columns alone, so
 // the host can build it while the data columns are still in flight over PCIe, and reuse it for several
 // outcome/regressor sets on the same panel.
@@ -975,6 +1074,7 @@ struct lfe_plan {
   int local_fe = -1;
   int big = 0;   // highest-cardinality FE: its entry list was built first
   int block_bits = 0;   // > 0: the other FEs' lists are ordered in L2 blocks of the big FE's codes (l2_block_bits)
+  bool det = false;     // LFE_OPT_DETERMINISTIC at creation: plain (key, other codes, perm) lists + CSR offsets
   const int32_t* codes[LFE_MAX_FE] = {nullptr};
   const double* weights = nullptr;
   std::vector<FEState> st;
@@ -1031,7 +1131,15 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
       LFE_REQUIRE(st[j].G >= 1, "lfe_demean: n_groups[%d] must be >= 1", j);
       st[j].identity = (F == 1) || prim_is_sorted(h, codes[j], n, s) != 0;   // F == 1 never projects
     }
-    if (F == 2 && !weighted && !st[0].identity && !st[1].identity &&
+    const bool det = h->opt_deterministic != 0;
+    LFE_REQUIRE(!det || !dist, "LFE_OPT_DETERMINISTIC is single-GPU only");
+    plan->det = det;
+    if (det) {
+      // every FE that projects needs its (sorted key, other codes, row permutation) list: F == 1 never projects, but
+      // its S0 is summed in list order too
+      for (int j = 0; j < F; ++j) st[j].identity = prim_is_sorted(h, codes[j], n, s) != 0;
+    }
+    if (!det && F == 2 && !weighted && !st[0].identity && !st[1].identity &&
         bits_for((uint64_t)(st[0].G - 1)) + bits_for((uint64_t)(st[1].G - 1)) <= 32) {
       // two FEs whose codes fit one 32-bit word together: every entry is the packed word
       // (big code << bs) | small code.  Sorting the words stably on the big code's bits gives the big FE's
@@ -1063,7 +1171,7 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
       B.key = B.key_buf; B.packed = true; B.pk = PackSpec{bs, 0, bmask, smask};
       M.key = M.key_buf; M.packed = true; M.pk = PackSpec{0, bs, smask, bmask};
       B.oth[sm] = nullptr; M.oth[big] = nullptr;
-    } else if (F == 2 && !weighted && !st[0].identity && !st[1].identity) {
+    } else if (!det && F == 2 && !weighted && !st[0].identity && !st[1].identity) {
       // two FEs, codes too wide to pack: sort (key, other code) pairs directly
       const int sm = 1 - big;
       FEState &B = st[big], &M = st[sm];
@@ -1146,11 +1254,18 @@ lfe_plan* demean_plan_create(lfe_ctx* h, const int32_t* const* codes, const int6
         DevBuf<double>& dst = weighted ? S.cnt_buf : S.nsum;
         if (weighted) S.cnt_buf.alloc(S.G, s);
         prim_u32_to_f64(h, cnt32, S.G, dst, s);
+        if (det) {   // CSR offsets of the groups in the sorted list: exclusive scan of the sizes, off[G] = n
+          S.off.alloc(S.G + 1, s);
+          S.off.zero();
+          CUDA_CHECK(cudaMemcpyAsync(S.off.p, cnt32, (size_t)S.G * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+          prim_exclusive_scan_u32(h, S.off, S.off, S.G + 1, nullptr, s);
+        }
       }
       if (weighted) {
         S.nsum.zero();
         ColPtrs cw; cw.col[0] = weights;
-        launch_groupsum<false>(h, 1, codes[j], S.G, cw, nullptr, n, S.nsum, 1, 0, s);
+        if (det) launch_det_s0<false>(h, 1, S, cw, nullptr, S.nsum, 1, 0, s);
+        else launch_groupsum<false>(h, 1, codes[j], S.G, cw, nullptr, n, S.nsum, 1, 0, s);
         S.cnt = S.cnt_buf;
       } else {
         S.cnt = S.nsum;
@@ -1226,7 +1341,12 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
       ColPtrs cp;
       for (int c = 0; c < nc; ++c) cp.col[c] = in[c0 + c];
-      if (F >= 2) {
+      if (plan->det) {
+        for (int j = 0; j < F; ++j) {
+          if (weighted) launch_det_s0<true>(h, nc, st[j], cp, weights, st[j].S0, Cp, c0, s);
+          else launch_det_s0<false>(h, nc, st[j], cp, nullptr, st[j].S0, Cp, c0, s);
+        }
+      } else if (F >= 2) {
         int64_t Gs[LFE_MAX_FE];
         double* accs[LFE_MAX_FE];
         for (int j = 0; j < F; ++j) { Gs[j] = st[j].G; accs[j] = st[j].S0; }
@@ -1245,7 +1365,8 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
         S.S0u_buf.alloc(S.G, s);
         S.S0u_buf.zero();
         ColPtrs cy; cy.col[0] = in[0];
-        launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
+        if (plan->det) launch_det_s0<false>(h, 1, S, cy, nullptr, S.S0u_buf, 1, 0, s);
+        else launch_groupsum<false>(h, 1, codes[j], S.G, cy, nullptr, n, S.S0u_buf, 1, 0, s);
         S.S0u = S.S0u_buf; S.ld_s0u = 1;
       } else {
         S.S0u = S.S0; S.ld_s0u = Cp;
@@ -1306,10 +1427,14 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
     ProjOthers o = others_of(j, false);
     // a very small FE is projected over the big FE's entry list with thread-private bins (k_proj_tiny)
     const int big = plan->big;
-    const bool tiny = j != big && n >= 65536 && S.G * (C < PJ_MAXNC ? C : PJ_MAXNC) <= PT_MAX_BINS;
+    const bool tiny = !plan->det && j != big && n >= 65536 && S.G * (C < PJ_MAXNC ? C : PJ_MAXNC) <= PT_MAX_BINS;
     for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
       int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
-      if (tiny) {
+      if (plan->det) {
+        o.stage_rows[0] = 0;   // (no staging: plain gathers)
+        if (weighted) launch_det_proj<true>(h, nc, S, o, Cp, c0, S.acc, Cp, c0, s);
+        else launch_det_proj<false>(h, nc, S, o, Cp, c0, S.acc, Cp, c0, s);
+      } else if (tiny) {
         if (weighted) launch_proj_tiny<true>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
         else launch_proj_tiny<false>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
       } else if (weighted) {
@@ -1372,7 +1497,8 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
         for (int oi = 1; oi + 1 < F; ++oi) {
           FEState& S = st[fe_order[oi]];
           ProjOthers o = others_of(fe_order[oi], true);
-          launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
+          if (plan->det) launch_det_proj<false>(h, 1, S, o, Cp, 0, S.acc_chk, 1, 0, s);
+          else launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
           if (dist && fe_order[oi] != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
           k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
                                                                              S.G, Cp, dmax);
@@ -1412,7 +1538,8 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
         FEState& S = st[j];
         if (F > 1) {
           ProjOthers o = others_of(j, true);
-          launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
+          if (plan->det) launch_det_proj<false>(h, 1, S, o, Cp, 0, S.acc_chk, 1, 0, s);
+          else launch_proj<false>(h, 1, S, o, n, Cp, 0, S.acc_chk, 1, 0, proj_smem, s);
           if (dist && j != local_fe) comm_allreduce(h, S.acc_chk, S.G, 0, s);
         }
         k_check<<<launch_blocks(h, ceil_div64(S.G, 256), 8), 256, 0, s>>>(S.alpha, S.acc_chk, S.S0u, S.ld_s0u, S.cnt,
@@ -1512,6 +1639,8 @@ void demean_plan_fit(lfe_ctx* h, lfe_plan* plan, const double* const* cols, int 
                      int ssc, int64_t n_obs, int64_t df_resid, double* beta_full_out, double* se_out, double* vcov_out,
                      double* stats_out, int* iterations_out, double* max_mean_out, int* converged_out,
                      int64_t* n_clusters_out, cudaStream_t s) {
+  LFE_REQUIRE(!plan->det || (vcov_kind & 0xff) != LFE_VCOV_CLUSTER,
+              "lfe_demean_plan_fit: deterministic clustered SEs go through lfe_demean_plan_run + lfe_resid_vcov");
   LFE_REQUIRE(C >= 1 && C <= TL_MAXC, "lfe_demean_plan_fit: %d columns unsupported (max %d); use lfe_demean_plan_run + "
               "lfe_gram + lfe_resid_vcov", C, TL_MAXC);
   TailRequest tr{vcov_kind, cl_codes, n_cl_groups, ssc, n_obs, df_resid, beta_full_out, se_out, vcov_out, stats_out,

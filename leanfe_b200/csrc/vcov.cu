@@ -146,10 +146,65 @@ __global__ void k_scale_se(const double* __restrict__ V, int k, double scale, co
   }
 }
 
+// deterministic mode: S[g][col0 + c] = sum over the rows of cluster g, in row order, of w x_c r -- one warp per cluster
+// walks its rows of the cluster-sorted permutation, fixed shuffle tree, plain stores (no floating-point atomics)
+template <int NC>
+__global__ void __launch_bounds__(256) k_det_scores(const uint32_t* __restrict__ off, int64_t G,
+                                                    const uint32_t* __restrict__ perm, ColPtrs X,
+                                                    const double* __restrict__ r, const double* __restrict__ w,
+                                                    double* __restrict__ S, int K, int col0) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < G; g += nwarp) {
+    double sum[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = 0.0;
+    const uint32_t e1 = off[g + 1];
+    for (uint32_t e = off[g] + lane; e < e1; e += 32) {
+      const size_t row = perm[e];
+      const double rw = w ? r[row] * w[row] : r[row];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sum[c] += X.col[c][row] * rw;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum[c] = warp_sum(sum[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) S[(size_t)g * K + col0 + c] = sum[c];
+    }
+  }
+}
+
 static void scores_meat(lfe_ctx* h, const int32_t* cl, int64_t G, const double* const* xcols, int k, const double* resid,
                         const double* w, int64_t n, double* meat_dev, cudaStream_t s, bool cl_local = false) {
   DevBuf<double> S((size_t)G * k, s);
   S.zero();
+  if (h->opt_deterministic && n > 0) {
+    LFE_REQUIRE(h->world == 1, "LFE_OPT_DETERMINISTIC is single-GPU only");
+    DevBuf<uint32_t> perm(n, s), off(G + 1, s);
+    off.zero();
+    prim_histogram(h, cl, n, G, off, s);
+    prim_exclusive_scan_u32(h, off, off, G + 1, nullptr, s);
+    prim_argsort_u32(h, (const uint32_t*)cl, n, bits_for((uint64_t)(G > 0 ? G - 1 : 0)), perm, nullptr, s);
+    const int blocks = launch_blocks(h, ceil_div64(G, 8), 8);
+    for (int c0 = 0; c0 < k; c0 += PJ_MAXNC) {
+      const int nc = k - c0 < PJ_MAXNC ? k - c0 : PJ_MAXNC;
+      ColPtrs cp;
+      for (int c = 0; c < nc; ++c) cp.col[c] = xcols[c0 + c];
+#define DSC_CASE(NC_) \
+  case NC_: k_det_scores<NC_><<<blocks, 256, 0, s>>>(off, G, perm, cp, resid, w, S, k, c0); break;
+      switch (nc) {
+        DSC_CASE(1) DSC_CASE(2) DSC_CASE(3) DSC_CASE(4) DSC_CASE(5) DSC_CASE(6) DSC_CASE(7) DSC_CASE(8)
+      }
+#undef DSC_CASE
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
+    std::vector<const double*> scd(k);
+    for (int c = 0; c < k; ++c) scd[c] = S.p + c;
+    gram_core(h, scd.data(), k, G, nullptr, nullptr, 0, meat_dev, s, k);
+    return;
+  }
   int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I);
   int blocks = launch_blocks(h, nchunk, 8);
   bool vec = (((uintptr_t)cl) & 15) == 0;
@@ -684,7 +739,7 @@ void resid_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t n, co
   LFE_REQUIRE(vcov_kind >= 0 && vcov_kind <= 2, "lfe_resid_vcov: unknown vcov kind %d", vcov_kind);
   LFE_REQUIRE(n >= 1 || h->world > 1, "lfe_resid_vcov: no rows");
   if (vcov_kind == LFE_VCOV_CLUSTER) LFE_REQUIRE(W >= 1 && W <= LFE_MAX_CLUSTER_WAYS, "lfe_resid_vcov: cluster_cols required (1..%d ways)", LFE_MAX_CLUSTER_WAYS);
-  if (vcov_kind == LFE_VCOV_CLUSTER && W == 1 && k >= 1 && k <= PJ_MAXNC && !resid_out) {
+  if (vcov_kind == LFE_VCOV_CLUSTER && W == 1 && k >= 1 && k <= PJ_MAXNC && !resid_out && !h->opt_deterministic) {
     fused_oneway_cluster(h, cols, k, n, beta_full, Binv, cl_codes[0], n_cl_groups[0], weights, ssc, n_obs, df_resid,
                          cl_local, se_out, vcov_out, stats_out, n_clusters_out, s);
     return;

@@ -370,3 +370,33 @@ def test_yoco_singular_design_takes_the_references_min_norm_fallback(golden_dir,
     assert abs(b[1]) < 1e-10 and abs(eb[1]) < 1e-10 and s[1] < 1e-12 and es[1] < 1e-12       # the dead column
     assert res.df_resid == int(g[f"ref_df_resid_{tag}"])
     assert res.rss == pytest.approx(float(g[f"ref_rss_{tag}"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("fes,vcov,cl,weighted", [("unit + time", "cluster", ["unit"], False), ("unit + time", "hc1", None, True),
+                                                   ("unit + time", "cluster", ["unit", "time"], False),
+                                                   ("unit + time + reg", "iid", None, False), ("unit", "cluster", ["time"], True)])
+def test_deterministic_mode_is_bit_identical_across_runs(fes, vcov, cl, weighted):
+    """deterministic=True (LFE_OPT_DETERMINISTIC): every group sum is taken in a fixed order, so two fits of the same
+    data agree in every bit -- and still match the oracle to the usual tolerances."""
+    from leanfe_b200 import leanfe
+    rng = np.random.default_rng(21)
+    n = 300_000
+    unit, time_, reg = rng.integers(0, 20_000, n), rng.integers(0, 40, n), rng.integers(0, 300, n)
+    a = rng.normal(size=20_000)
+    d = dict(unit=unit, time=time_, reg=reg, w=rng.uniform(0.5, 2.0, n))
+    d["x1"], d["x2"], d["x3"] = (rng.normal(size=n) + 0.4 * a[unit] for _ in range(3))
+    d["y"] = d["x1"] - 0.5 * d["x2"] + 0.25 * d["x3"] + a[unit] + 0.05 * time_ + rng.normal(size=n) * (1 + 0.3 * (unit % 4))
+    kw = dict(formula=f"y ~ x1 + x2 + x3 | {fes}", vcov=vcov, cluster_cols=cl, weights="w" if weighted else None,
+              strategy="alt_proj" if "+" in fes else "demean")
+    dd = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    runs = [leanfe(dd, deterministic=True, **kw) for _ in range(3)]
+    for r in runs[1:]:
+        assert list(r.coefs.values()) == list(runs[0].coefs.values())               # exact equality
+        assert list(r.std_errors.values()) == list(runs[0].std_errors.values())
+        assert r.rss == runs[0].rss and r.iterations == runs[0].iterations
+    _check(runs[0], O.leanfe_oracle(d, **kw))
+    # the default (atomics) path agrees to rounding
+    fast = leanfe(dd, **kw)
+    np.testing.assert_allclose(list(fast.coefs.values()), list(runs[0].coefs.values()), rtol=1e-11)
+    with pytest.raises(NotImplementedError):
+        leanfe(dd, formula="y ~ x1 | unit + time", strategy="compress", deterministic=True)
