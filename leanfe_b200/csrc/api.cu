@@ -171,20 +171,24 @@ void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, 
   NCCL_CHECK(g_nccl.allreduce(buf, buf, (size_t)count, nccl_type, op, h->nccl_comm, s));
 }
 
-// all-to-all with per-peer byte counts: one grouped round of ncclSend / ncclRecv (self included)
-void comm_alltoallv_bytes(lfe_ctx* h, const void* send, const int64_t* send_off, const int64_t* send_cnt, void* recv,
-                          const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s) {
-  if (h->world <= 1) return;
+// all-to-all of K buffers with per-peer byte counts ([k * world + r]) in ONE grouped round of ncclSend / ncclRecv
+// (self included): NCCL fuses the K x world transfers into one launch
+void comm_alltoallv_multi(lfe_ctx* h, int K, const void* const* send, const int64_t* send_off, const int64_t* send_cnt,
+                          void* const* recv, const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s) {
+  if (h->world <= 1 || K <= 0) return;
   if (!g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end)
     LFE_THROW(LFE_ERR_NCCL, "libnccl has no ncclSend/ncclRecv (need NCCL >= 2.7)");
   h->n_collectives += 1;
   enum { NCCL_UINT8 = 1 };
   NCCL_CHECK(g_nccl.group_start());
-  for (int r = 0; r < h->world; ++r) {
-    if (send_cnt[r] > 0)
-      NCCL_CHECK(g_nccl.send((void*)((const char*)send + send_off[r]), (size_t)send_cnt[r], NCCL_UINT8, r, h->nccl_comm, s));
-    if (recv_cnt[r] > 0)
-      NCCL_CHECK(g_nccl.recv((char*)recv + recv_off[r], (size_t)recv_cnt[r], NCCL_UINT8, r, h->nccl_comm, s));
+  for (int k = 0; k < K; ++k) {
+    for (int r = 0; r < h->world; ++r) {
+      const size_t i = (size_t)k * h->world + r;
+      if (send_cnt[i] > 0)
+        NCCL_CHECK(g_nccl.send((void*)((const char*)send[k] + send_off[i]), (size_t)send_cnt[i], NCCL_UINT8, r, h->nccl_comm, s));
+      if (recv_cnt[i] > 0)
+        NCCL_CHECK(g_nccl.recv((char*)recv[k] + recv_off[i], (size_t)recv_cnt[i], NCCL_UINT8, r, h->nccl_comm, s));
+    }
   }
   NCCL_CHECK(g_nccl.group_end());
 }

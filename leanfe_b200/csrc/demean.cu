@@ -190,6 +190,60 @@ __global__ void __launch_bounds__(PJ_T, 2) k_proj(const int32_t* __restrict__ ke
   }
 }
 
+// Packed two-FE projection whose other table is SMALL (the 500-period table of c2 / c5 while projecting on unit):
+// every entry gathers one table row from shared memory at random.  With the plain staged copy (k_proj) the 128-bit
+// loads of a quarter-warp land on random bank quads -- row r, piece p sits on quad (3 r + p) mod 8 for 48-byte rows
+// -- so a warp-wide LDS.128 takes ~8-11 wavefronts instead of 4 and the kernel is bound by the shared-memory data
+// pipe (84 % busy, ncu r1).  Here every 16-byte piece is stored R times, once per bank quad: piece p of row r owns the
+// R consecutive 16-byte slots (r NP + p) R .. + R - 1 and lane l reads slot (l + p) mod R.  For R = 8 the eight lanes
+// of a quarter-warp therefore always hit eight different bank quads, whatever rows they gather: no conflicts, by
+// construction.  (R = 4 / 2 when 8 copies do not fit: conflicts only between lanes l and l + R.)  One 512-thread CTA
+// per SM owns the replicated table (500 rows x 3 pieces x 128 B = 192 KB at c2).
+constexpr int PR_T = 512;
+template <int NC, int R>
+__global__ void __launch_bounds__(PR_T, 1) k_proj_rep(const uint32_t* __restrict__ words, const double* __restrict__ tab,
+                                                      int rows, int ldc, int64_t n, double* __restrict__ acc, int ld_acc,
+                                                      int acc_col0, PackSpec pk) {
+  constexpr int NP = (NC + 1) / 2;       // 16-byte pieces per row (an odd NC reads the zero pad column too)
+  constexpr int PER_THREAD = PJ_I * PJ_NB;
+  extern __shared__ __align__(16) double2 rep[];
+  for (int idx = threadIdx.x; idx < rows * NP * R; idx += PR_T) {
+    const int p = (idx / R) % NP, row = idx / (R * NP);
+    rep[idx] = *reinterpret_cast<const double2*>(tab + (size_t)row * ldc + 2 * p);
+  }
+  __syncthreads();
+  const int q = threadIdx.x & (R - 1);
+  const int64_t nchunk = ceil_div64(n, (int64_t)PR_T * PER_THREAD);
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    const int64_t tbase = (ch * PR_T + threadIdx.x) * PER_THREAD;
+    int cur = -1;
+    double run[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) run[c] = 0.0;
+#pragma unroll 1
+    for (int b = 0; b < PJ_NB; ++b) {
+      const int64_t base = tbase + b * PJ_I;
+      int pw[PJ_I], k[PJ_I];
+      double v[PJ_I][NC];
+      load4_i32(reinterpret_cast<const int32_t*>(words), base, n, true, pw);   // (-1 words beyond n)
+#pragma unroll
+      for (int e = 0; e < PJ_I; ++e) {
+        const bool valid = base + e < n;
+        k[e] = valid ? (int)(((uint32_t)pw[e] >> pk.kshift) & pk.kmask) : -1;
+        const int oc = valid ? (int)(((uint32_t)pw[e] >> pk.oshift) & pk.omask) : 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const double2 t = rep[(oc * NP + p) * R + ((q + p) & (R - 1))];
+          v[e][2 * p] = valid ? t.x : 0.0;
+          if (2 * p + 1 < NC) v[e][2 * p + 1] = valid ? t.y : 0.0;
+        }
+      }
+      run_fold<NC>(cur, run, k, v, acc, ld_acc, acc_col0);
+    }
+    warp_flush<NC>(cur, run, acc, ld_acc, acc_col0);
+  }
+}
+
 // Packed two-FE projection whose other table lives in global memory (L2): lanes cooperate on the gathered rows.
 // In k_proj every lane gathers its own 8*NC-byte row with up to NC/2 128-bit loads, so a warp-wide load touches
 // 32 different cache lines and the kernel is bound by L1TEX wavefronts (87 % of peak at c2, ncu r1), one per
@@ -846,6 +900,39 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
     h->n_launches += 1;
     h->n_sweep_launches += 1;
     return;
+  }
+  if (st.packed && oth.n == 1 && oth.stage_rows[0] > 0 && n >= 65536 && (ldc & 1) == 0 && (col0 & 1) == 0 &&
+      aligned16(oth.alpha[0]) && aligned16(st.key) && col0 + 2 * ((nc + 1) / 2) <= ldc) {
+    // small other table: bank-conflict-free replicated copy in shared memory (k_proj_rep)
+    static const bool no_rep = getenv("LFE_NO_PROJ_REP") != nullptr;
+    const int rows = oth.stage_rows[0], np = (nc + 1) / 2;
+    const size_t budget = (size_t)(h->smem_optin > 0 ? h->smem_optin : 0) - 1024;
+    int R = 8;
+    while (R >= 2 && (size_t)rows * np * R * 16 > budget) R >>= 1;
+    if (R >= 2 && !no_rep) {
+      const size_t rsmem = (size_t)rows * np * R * 16;
+      const int rb = launch_blocks(h, ceil_div64(n, (int64_t)PR_T * PJ_I * PJ_NB), 1);
+#define PR_LAUNCH(NC_, R_)                                                                                           \
+  do {                                                                                                               \
+    CUDA_CHECK(cudaFuncSetAttribute(k_proj_rep<NC_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)); \
+    k_proj_rep<NC_, R_><<<rb, PR_T, rsmem, s>>>((const uint32_t*)st.key, oth.alpha[0] + col0, rows, ldc, n, acc,    \
+                                                ld_acc, acc_col0, st.pk);                                            \
+  } while (0)
+#define PR_CASE(NC_)                                                                                  \
+  case NC_:                                                                                           \
+    if (R == 8) PR_LAUNCH(NC_, 8); else if (R == 4) PR_LAUNCH(NC_, 4); else PR_LAUNCH(NC_, 2);        \
+    break;
+      switch (nc) {
+        PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7) PR_CASE(8)
+        default: LFE_THROW(LFE_ERR_ARG, "launch_proj: nc=%d", nc);
+      }
+#undef PR_CASE
+#undef PR_LAUNCH
+      KERNEL_CHECK();
+      h->n_launches += 1;
+      h->n_sweep_launches += 1;
+      return;
+    }
   }
 #define PJ_CASE(NC_)                                                                                          \
   case NC_:                                                                                                   \

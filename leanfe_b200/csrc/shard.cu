@@ -15,8 +15,8 @@
 #include "common.cuh"
 
 void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);   // api.cu
-void comm_alltoallv_bytes(lfe_ctx* h, const void* send, const int64_t* send_off, const int64_t* send_cnt, void* recv,
-                          const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s);          // api.cu
+void comm_alltoallv_multi(lfe_ctx* h, int K, const void* const* send, const int64_t* send_off, const int64_t* send_cnt,
+                          void* const* recv, const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s);   // api.cu
 
 constexpr int SHARD_MAX_WORLD = 256;
 constexpr int CUT_T = 1024;
@@ -151,33 +151,47 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
   const int world = h->world;
   PhaseTimer t(h, s, 14);
   int64_t n_recv = 0, n_send = 0;
-  std::vector<int64_t> soff(world), roff(world), sb(world), rb(world), sbo(world), rbo(world);
+  std::vector<int64_t> soff(world), roff(world);
   for (int r = 0; r < world; ++r) { soff[r] = n_send; n_send += send_counts[r]; roff[r] = n_recv; n_recv += recv_counts[r]; }
   LFE_REQUIRE(n_send == n, "lfe_shard_exchange: send_counts sum to %lld, n = %lld", (long long)n_send, (long long)n);
-  size_t max_es = 1;
-  for (int c = 0; c < K; ++c) max_es = dtype_size(dtypes[c]) > max_es ? dtype_size(dtypes[c]) : max_es;
-  DevBuf<unsigned char> stage(world > 1 ? (size_t)(n > 0 ? n : 1) * max_es : 0, s);
   const int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 8);
-  for (int c = 0; c < K; ++c) {
-    const size_t es = dtype_size(dtypes[c]);
-    if (world == 1) {
+  if (world == 1) {
+    for (int c = 0; c < K; ++c) {
+      const size_t es = dtype_size(dtypes[c]);
       if (n > 0 && cols_out[c] != cols_in[c])
         CUDA_CHECK(cudaMemcpyAsync(cols_out[c], cols_in[c], (size_t)n * es, cudaMemcpyDeviceToDevice, s));
-    } else {
+    }
+  } else {
+    // all columns are gathered into send order first, then leave in ONE grouped round of ncclSend / ncclRecv
+    // (K x world transfers fused by NCCL into one launch: large messages to every peer at once over NVSwitch,
+    // instead of K latency-bound rounds)
+    std::vector<int64_t> col_off(K + 1, 0);
+    for (int c = 0; c < K; ++c) col_off[c + 1] = col_off[c] + (((int64_t)(n > 0 ? n : 1) * (int64_t)dtype_size(dtypes[c]) + 255) & ~(int64_t)255);
+    DevBuf<unsigned char> stage((size_t)col_off[K], s);
+    std::vector<const void*> sbuf(K);
+    std::vector<void*> rbuf(K);
+    std::vector<int64_t> sb((size_t)K * world), rb((size_t)K * world), sbo((size_t)K * world), rbo((size_t)K * world);
+    for (int c = 0; c < K; ++c) {
+      const size_t es = dtype_size(dtypes[c]);
+      unsigned char* st = stage.p + col_off[c];
       if (n > 0) {
         const uint32_t* ord = (const uint32_t*)order;
-        if (es == 8) k_gather_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, (uint64_t*)stage.p);
-        else if (es == 4) k_gather_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, (uint32_t*)stage.p);
-        else k_gather_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, (uint8_t*)stage.p);
+        if (es == 8) k_gather_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, (uint64_t*)st);
+        else if (es == 4) k_gather_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, (uint32_t*)st);
+        else k_gather_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, (uint8_t*)st);
         KERNEL_CHECK();
         h->n_launches += 1;
       }
+      sbuf[c] = st;
+      rbuf[c] = cols_out[c];
       for (int r = 0; r < world; ++r) {
-        sbo[r] = soff[r] * (int64_t)es; sb[r] = send_counts[r] * (int64_t)es;
-        rbo[r] = roff[r] * (int64_t)es; rb[r] = recv_counts[r] * (int64_t)es;
+        sbo[(size_t)c * world + r] = soff[r] * (int64_t)es; sb[(size_t)c * world + r] = send_counts[r] * (int64_t)es;
+        rbo[(size_t)c * world + r] = roff[r] * (int64_t)es; rb[(size_t)c * world + r] = recv_counts[r] * (int64_t)es;
       }
-      comm_alltoallv_bytes(h, stage.p, sbo.data(), sb.data(), cols_out[c], rbo.data(), rb.data(), s);
     }
+    comm_alltoallv_multi(h, K, sbuf.data(), sbo.data(), sb.data(), rbuf.data(), rbo.data(), rb.data(), s);
+  }
+  for (int c = 0; c < K; ++c) {
     if (i32_sub && i32_sub[c] != 0 && n_recv > 0) {
       LFE_REQUIRE(dtypes[c] == LFE_I32, "lfe_shard_exchange: i32_sub on a non-int32 column");
       k_sub_i32<<<launch_blocks(h, ceil_div64(n_recv, 256 * 8), 8), 256, 0, s>>>((int32_t*)cols_out[c], n_recv,
