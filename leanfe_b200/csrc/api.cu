@@ -118,6 +118,7 @@ typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cu
 typedef const char* (*nccl_errstr_fn)(int);
 typedef int (*nccl_sendrecv_fn)(void*, size_t, int, int, void*, cudaStream_t);   // ncclSend (const buf) / ncclRecv
 typedef int (*nccl_group_fn)(void);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 static struct {
   void* lib = nullptr;
   nccl_get_uid_fn get_uid = nullptr;
@@ -127,6 +128,7 @@ static struct {
   nccl_errstr_fn errstr = nullptr;
   nccl_sendrecv_fn send = nullptr, recv = nullptr;
   nccl_group_fn group_start = nullptr, group_end = nullptr;
+  nccl_allgather_fn allgather = nullptr;
 } g_nccl;
 enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
@@ -149,6 +151,7 @@ static void load_nccl() {
   g_nccl.recv = (nccl_sendrecv_fn)dlsym(g_nccl.lib, "ncclRecv");
   g_nccl.group_start = (nccl_group_fn)dlsym(g_nccl.lib, "ncclGroupStart");
   g_nccl.group_end = (nccl_group_fn)dlsym(g_nccl.lib, "ncclGroupEnd");
+  g_nccl.allgather = (nccl_allgather_fn)dlsym(g_nccl.lib, "ncclAllGather");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy)
     LFE_THROW(LFE_ERR_NCCL, "libnccl is missing required symbols");
 }
@@ -191,6 +194,14 @@ void comm_alltoallv_multi(lfe_ctx* h, int K, const void* const* send, const int6
     }
   }
   NCCL_CHECK(g_nccl.group_end());
+}
+
+// all-gather of `bytes` bytes per rank (device buffers); false when the symbol is missing
+bool comm_allgather_bytes(lfe_ctx* h, const void* send, void* recv, size_t bytes, cudaStream_t s) {
+  if (h->world <= 1 || !g_nccl.allgather) return false;
+  h->n_collectives += 1;
+  NCCL_CHECK(g_nccl.allgather(send, recv, bytes, 1 /*ncclUint8*/, h->nccl_comm, s));
+  return true;
 }
 
 void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int64_t* cuts_out, int64_t* send_counts_out,
@@ -242,6 +253,9 @@ int lfe_destroy(lfe_handle h) {
   drain_timers(h);
   for (auto e : h->free_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
+  for (size_t r = 0; r < h->p2p.peer_base.size(); ++r)
+    if ((int)r != h->rank && h->p2p.peer_base[r]) cudaIpcCloseMemHandle(h->p2p.peer_base[r]);
+  if (h->p2p.base) cudaFree(h->p2p.base);
   h->last_counts.release();
   delete h;
   LFE_API_END

@@ -83,6 +83,15 @@ struct lfe_ctx {
   } last_counts;
   int64_t last_counts_G = -1;
   const void* last_counts_codes = nullptr;
+  // peer-to-peer receive arena of the row repartition (shard.cu): cudaMalloc'ed, exported with CUDA IPC, written
+  // directly by the other ranks' push kernels over NVLink
+  struct P2P {
+    void* base = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> peer_base;          // [rank] mapped arena of every peer (own: base)
+    std::vector<std::string> peer_handle;  // [rank] the IPC handle bytes currently mapped ("" = none)
+    bool disabled = false;                 // IPC unavailable: the grouped ncclSend/ncclRecv path is used
+  } p2p;
   // lfe_set_option
   int opt_columns_hint = 0;                 // columns per demean run (0 = unknown): sizes the L2 blocks of the entry lists
   int64_t opt_l2_block_bytes = 48ll << 20;  // a table slice this large is expected to stay L2-resident while it is gathered

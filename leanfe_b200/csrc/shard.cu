@@ -15,8 +15,35 @@
 #include "common.cuh"
 
 void comm_allreduce_int(lfe_ctx* h, void* buf, int64_t count, int kind, int op, cudaStream_t s);   // api.cu
+bool comm_allgather_bytes(lfe_ctx* h, const void* send, void* recv, size_t bytes, cudaStream_t s);          // api.cu
 void comm_alltoallv_multi(lfe_ctx* h, int K, const void* const* send, const int64_t* send_off, const int64_t* send_cnt,
                           void* const* recv, const int64_t* recv_off, const int64_t* recv_cnt, cudaStream_t s);   // api.cu
+
+// LFE_TRACE_SHARD=1: device time of every stage of the repartition (CUDA events, printed by rank 0)
+struct ShardTrace {
+  bool on;
+  int rank;
+  cudaStream_t s;
+  std::vector<std::pair<const char*, cudaEvent_t>> ev;
+  ShardTrace(lfe_ctx* h, cudaStream_t s_) : on(getenv("LFE_TRACE_SHARD") != nullptr), rank(h->rank), s(s_) { mark("start"); }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back({name, e});
+  }
+  ~ShardTrace() {
+    if (!on) return;
+    cudaEventSynchronize(ev.back().second);
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      if (rank == 0) fprintf(stderr, "lfe shard trace: %-28s %.3f ms\n", ev[i].first, ms);
+    }
+    for (auto& e : ev) cudaEventDestroy(e.second);
+  }
+};
 
 constexpr int SHARD_MAX_WORLD = 256;
 constexpr int CUT_T = 1024;
@@ -94,6 +121,142 @@ __global__ void __launch_bounds__(256) k_sub_i32(int32_t* __restrict__ p, int64_
     p[i] -= sub;
 }
 
+// ---- the exchange itself, over NVLink peer memory ------------------------------------------------------------
+// NCCL's send/recv pairs stage every chunk through intermediate FIFO buffers: 188 GB/s per GPU on this box for
+// the 3.6 GB each rank sends at c5 (4 ranks), a quarter of what the links carry.  Here every rank owns a receive
+// ARENA (cudaMalloc, exported with CUDA IPC, mapped by every peer once and reused across fits) and the gather
+// kernel of the sender stores each row straight into the owner's arena through NVSwitch: gather and transfer are
+// one kernel, nothing is staged, and the stores of a warp are 256 contiguous bytes of the destination column.
+// Protocol per exchange (all stream-ordered on `s`): (1) every rank sizes its arena and all-gathers
+// {IPC handle, arena bytes, rows it will receive, where each source's rows start} -- this all-gather is also the
+// barrier that says "my arena is free again"; (2) push kernels, one per column; (3) a second tiny all-gather = "all
+// pushes have landed"; (4) local copy of the arena columns to the caller's outputs.
+constexpr int P2P_MAX_WORLD = 16;
+struct PushSpec {
+  unsigned char* col[P2P_MAX_WORLD];    // destination column start in rank d's arena
+  long long soff[P2P_MAX_WORLD + 1];    // my send order: rows [soff[d], soff[d+1]) go to rank d
+  long long row0[P2P_MAX_WORLD];        // first row of MY block inside rank d's column
+  int world;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_by(const T* __restrict__ src, const uint32_t* __restrict__ order, int64_t n,
+                                                 PushSpec sp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int d = 0;
+#pragma unroll 1
+    while (d + 1 < sp.world && i >= sp.soff[d + 1]) ++d;
+    reinterpret_cast<T*>(sp.col[d])[sp.row0[d] + (i - sp.soff[d])] = __ldg(src + __ldcs(order + i));
+  }
+}
+
+struct P2PInfo {                        // what every rank publishes before an exchange
+  cudaIpcMemHandle_t handle;
+  long long arena_bytes, n_recv;
+  long long roff[P2P_MAX_WORLD];        // roff[r] = first row of source r's block in my columns
+};
+
+size_t dtype_size(int dt);
+
+// returns false when the peer-memory path is unavailable (caller falls back to NCCL send/recv)
+static bool exchange_p2p(lfe_ctx* h, const int32_t* order, const int64_t* send_counts, const int64_t* recv_counts,
+                         const void* const* cols_in, const int* dtypes, int K, int64_t n, void* const* cols_out,
+                         ShardTrace& tr, cudaStream_t s) {
+  static const bool p2p_off = getenv("LFE_NO_P2P") != nullptr;
+  const int world = h->world, me = h->rank;
+  if (p2p_off || h->p2p.disabled || world > P2P_MAX_WORLD) return false;
+  auto col_bytes = [&](int64_t rows, int c) { return ((int64_t)(rows > 0 ? rows : 1) * (int64_t)dtype_size(dtypes[c]) + 255) & ~(int64_t)255; };
+  int64_t n_recv = 0;
+  P2PInfo mine;
+  memset(&mine, 0, sizeof(mine));
+  for (int r = 0; r < world; ++r) { mine.roff[r] = n_recv; n_recv += recv_counts[r]; }
+  int64_t need = 0;
+  for (int c = 0; c < K; ++c) need += col_bytes(n_recv, c);
+  if ((size_t)need > h->p2p.bytes) {
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (h->p2p.base) cudaFree(h->p2p.base);
+    h->p2p.base = nullptr;
+    h->p2p.bytes = 0;
+    const size_t want = (size_t)need + (size_t)need / 4 + (1 << 20);
+    if (cudaMalloc(&h->p2p.base, want) != cudaSuccess) { (void)cudaGetLastError(); h->p2p.disabled = true; }
+    else h->p2p.bytes = want;
+  }
+  if (!h->p2p.disabled && cudaIpcGetMemHandle(&mine.handle, h->p2p.base) != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->p2p.disabled = true;
+  }
+  mine.arena_bytes = h->p2p.disabled ? -1 : (long long)h->p2p.bytes;
+  mine.n_recv = n_recv;
+  // (1) publish / learn the arenas: doubles as the "arena free" barrier
+  DevBuf<P2PInfo> dmine(1, s), dall(world, s);
+  CUDA_CHECK(cudaMemcpyAsync(dmine.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+  if (!comm_allgather_bytes(h, dmine.p, dall.p, sizeof(P2PInfo), s)) { h->p2p.disabled = true; return false; }
+  std::vector<P2PInfo> all(world);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), dall.p, sizeof(P2PInfo) * world, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int r = 0; r < world; ++r)
+    if (all[r].arena_bytes < 0) { h->p2p.disabled = true; return false; }   // the same decision on every rank
+  h->p2p.peer_base.resize(world, nullptr);
+  h->p2p.peer_handle.resize(world);
+  for (int r = 0; r < world; ++r) {
+    if (r == me) { h->p2p.peer_base[r] = h->p2p.base; continue; }
+    const std::string hb((const char*)&all[r].handle, sizeof(cudaIpcMemHandle_t));
+    if (h->p2p.peer_handle[r] != hb) {
+      if (h->p2p.peer_base[r]) cudaIpcCloseMemHandle(h->p2p.peer_base[r]);
+      h->p2p.peer_base[r] = nullptr;
+      h->p2p.peer_handle[r].clear();
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        LFE_THROW(LFE_ERR_CUDA, "lfe_shard_exchange: cudaIpcOpenMemHandle failed for rank %d (set LFE_NO_P2P=1 to use "
+                  "the NCCL send/recv path)", r);
+      }
+      h->p2p.peer_base[r] = ptr;
+      h->p2p.peer_handle[r] = hb;
+    }
+  }
+  tr.mark("exchange: publish arenas");
+  // (2) push every column straight into its owner's arena
+  const int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 16);
+  std::vector<int64_t> peer_off(world, 0);     // running column offset inside each peer's arena
+  for (int c = 0; c < K; ++c) {
+    const size_t es = dtype_size(dtypes[c]);
+    PushSpec sp;
+    sp.world = world;
+    int64_t acc_rows = 0;
+    for (int d = 0; d < world; ++d) {
+      sp.col[d] = (unsigned char*)h->p2p.peer_base[d] + peer_off[d];
+      sp.soff[d] = acc_rows;
+      acc_rows += send_counts[d];
+      sp.row0[d] = all[d].roff[me];
+      peer_off[d] += col_bytes(all[d].n_recv, c);
+    }
+    sp.soff[world] = acc_rows;
+    if (n > 0) {
+      const uint32_t* ord = (const uint32_t*)order;
+      if (es == 8) k_push_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, sp);
+      else if (es == 4) k_push_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, sp);
+      else k_push_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, sp);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    }
+  }
+  tr.mark("exchange: push over NVLink");
+  // (3) every rank's pushes have completed when this collective completes
+  DevBuf<unsigned char> tok(1, s), toks(world, s);
+  tok.zero();
+  comm_allgather_bytes(h, tok.p, toks.p, 1, s);
+  // (4) arena -> caller's columns
+  int64_t off = 0;
+  for (int c = 0; c < K; ++c) {
+    if (n_recv > 0)
+      CUDA_CHECK(cudaMemcpyAsync(cols_out[c], (unsigned char*)h->p2p.base + off, (size_t)n_recv * dtype_size(dtypes[c]),
+                                 cudaMemcpyDeviceToDevice, s));
+    off += col_bytes(n_recv, c);
+  }
+  tr.mark("exchange: barrier + copy out");
+  return true;
+}
+
 void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int64_t* cuts_out, int64_t* send_counts_out,
                      int64_t* recv_counts_out, int32_t* order_out, cudaStream_t s) {
   const int world = h->world, rank = h->rank;
@@ -106,13 +269,17 @@ void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int
     if (n > 0) prim_iota_u32((uint32_t*)order_out, n, s);
     return;
   }
+  ShardTrace tr(h, s);
   DevBuf<uint32_t> counts(G > 0 ? G : 1, s);
   counts.zero();
   if (n > 0 && G > 0) prim_histogram(h, codes, n, G, counts, s);
+  tr.mark("plan: histogram");
   comm_allreduce_int(h, counts.p, G, 0, 0, s);
+  tr.mark("plan: all-reduce counts");
   DevBuf<long long> cuts(world + 1, s);
   k_balanced_cuts<<<1, CUT_T, 0, s>>>(counts, G, world, cuts);
   KERNEL_CHECK();
+  tr.mark("plan: balanced cuts");
   DevBuf<unsigned long long> mat((size_t)world * world, s);   // mat[src][dst] = rows src sends to dst
   mat.zero();
   DevBuf<uint32_t> dest(n > 0 ? n : 1, s);
@@ -123,7 +290,9 @@ void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int
     prim_argsort_u32(h, dest, n, bits_for((uint64_t)(world - 1)), (uint32_t*)order_out, nullptr, s);
   }
   h->n_launches += 2;
+  tr.mark("plan: destinations + argsort");
   comm_allreduce_int(h, mat.p, (int64_t)world * world, 1, 0, s);
+  tr.mark("plan: all-reduce count matrix");
   std::vector<unsigned long long> hm((size_t)world * world);
   std::vector<long long> hc(world + 1);
   CUDA_CHECK(cudaMemcpyAsync(hm.data(), mat.p, hm.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -136,7 +305,7 @@ void shard_plan_impl(lfe_ctx* h, const int32_t* codes, int64_t n, int64_t G, int
   }
 }
 
-static size_t dtype_size(int dt) {
+size_t dtype_size(int dt) {
   switch (dt) {
     case LFE_F64: case LFE_I64: case LFE_U64: return 8;
     case LFE_I32: case LFE_U32: return 4;
@@ -150,6 +319,7 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
                          void* const* cols_out, cudaStream_t s) {
   const int world = h->world;
   PhaseTimer t(h, s, 14);
+  ShardTrace tr(h, s);
   int64_t n_recv = 0, n_send = 0;
   std::vector<int64_t> soff(world), roff(world);
   for (int r = 0; r < world; ++r) { soff[r] = n_send; n_send += send_counts[r]; roff[r] = n_recv; n_recv += recv_counts[r]; }
@@ -161,8 +331,10 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
       if (n > 0 && cols_out[c] != cols_in[c])
         CUDA_CHECK(cudaMemcpyAsync(cols_out[c], cols_in[c], (size_t)n * es, cudaMemcpyDeviceToDevice, s));
     }
+  } else if (exchange_p2p(h, order, send_counts, recv_counts, cols_in, dtypes, K, n, cols_out, tr, s)) {
+    // moved by the push kernels over peer memory
   } else {
-    // all columns are gathered into send order first, then leave in ONE grouped round of ncclSend / ncclRecv
+    // fallback: all columns are gathered into send order first, then leave in ONE grouped round of ncclSend / ncclRecv
     // (K x world transfers fused by NCCL into one launch: large messages to every peer at once over NVSwitch,
     // instead of K latency-bound rounds)
     std::vector<int64_t> col_off(K + 1, 0);
@@ -189,7 +361,9 @@ void shard_exchange_impl(lfe_ctx* h, const int32_t* order, const int64_t* send_c
         rbo[(size_t)c * world + r] = roff[r] * (int64_t)es; rb[(size_t)c * world + r] = recv_counts[r] * (int64_t)es;
       }
     }
+    tr.mark("exchange: gathers");
     comm_alltoallv_multi(h, K, sbuf.data(), sbo.data(), sb.data(), rbuf.data(), rbo.data(), rb.data(), s);
+    tr.mark("exchange: grouped send/recv");
   }
   for (int c = 0; c < K; ++c) {
     if (i32_sub && i32_sub[c] != 0 && n_recv > 0) {
