@@ -255,6 +255,13 @@ __global__ void __launch_bounds__(PR_T, 1) k_proj_rep(const uint32_t* __restrict
 // shuffle scan before the last flush -- the same run-merging as k_proj, at quarter-warp granularity.
 constexpr int PQ_E = 16;   // entries per row group per round (one 128-bit word load per lane when LPR = 4)
 constexpr int PQ_R = 2;    // rounds per chunk: a row group owns 32 consecutive entries
+// lanes per row: 1 (NC <= 2), 2 (NC <= 4), 4 (NC <= 8), 8 (NC <= 16: c5's 11 columns in ONE pass -- the gathers are
+// row-granular, so a second column batch costs as much as the first); entries per round: every lane holds >= 4 words
+template <int NC>
+struct QuadCfg {
+  static constexpr int LPR = NC <= 2 ? 1 : (NC <= 4 ? 2 : (NC <= 8 ? 4 : 8));
+  static constexpr int E = LPR <= 4 ? PQ_E : 4 * LPR;
+};
 
 // one round of a row group: PQ_E entries folded into the open run (cur, r0, r1).  FULL: all entries exist.
 // VEC: table rows are 16-byte aligned (a lane that owns two columns loads them as one double2).
@@ -263,9 +270,10 @@ __device__ __forceinline__ void quad_round(const uint32_t* __restrict__ words, c
                                            int64_t ebase, int64_t n, int ldc, const PackSpec& pk, int p,
                                            int g, int c0, double* __restrict__ acc, int ld_acc, int acc_col0,
                                            int& cur, double& r0, double& r1) {
-  constexpr int WPL = PQ_E / LPR;            // entry words held by a lane per round
+  constexpr int E = QuadCfg<NC>::E;
+  constexpr int WPL = E / LPR;               // entry words held by a lane per round
   const int ncl = NC - c0 >= 2 ? 2 : (NC - c0 == 1 ? 1 : 0);   // columns this lane owns
-  const int rem = FULL ? PQ_E : (int)(n - ebase < (int64_t)PQ_E ? n - ebase : (int64_t)PQ_E);   // may be <= 0
+  const int rem = FULL ? E : (int)(n - ebase < (int64_t)E ? n - ebase : (int64_t)E);   // may be <= 0
   uint32_t mine[WPL];
 #pragma unroll
   for (int q = 0; q < WPL / 4; ++q) {
@@ -279,7 +287,7 @@ __device__ __forceinline__ void quad_round(const uint32_t* __restrict__ words, c
     }
   }
 #pragma unroll
-  for (int h0 = 0; h0 < PQ_E; h0 += 8) {
+  for (int h0 = 0; h0 < E; h0 += 8) {
     int k[8];
     double v0[8], v1[8];
     bool same = true;
@@ -327,9 +335,10 @@ template <int NC, bool VEC>
 __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__ words, const double* __restrict__ tab,
                                                     int64_t n, int ldc, double* __restrict__ acc, int ld_acc,
                                                     int acc_col0, PackSpec pk) {
-  constexpr int LPR = NC <= 2 ? 1 : (NC <= 4 ? 2 : 4);
+  constexpr int LPR = QuadCfg<NC>::LPR;
   constexpr int NG = 32 / LPR;
-  constexpr int GCH = PQ_E * PQ_R;           // entries per row group per chunk
+  constexpr int PQ_EE = QuadCfg<NC>::E;
+  constexpr int GCH = PQ_EE * PQ_R;          // entries per row group per chunk
   constexpr int WCH = NG * GCH;              // entries per warp per chunk
   const int lane = threadIdx.x & 31;
   const int p = lane % LPR, g = lane / LPR;
@@ -344,12 +353,12 @@ __global__ void __launch_bounds__(PJ_T, 3) k_proj_q(const uint32_t* __restrict__
     if ((ch + 1) * WCH <= n) {
 #pragma unroll 1
       for (int r = 0; r < PQ_R; ++r)
-        quad_round<NC, LPR, true, VEC>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, p, g, c0, acc, ld_acc,
+        quad_round<NC, LPR, true, VEC>(words, tab, gbase + (int64_t)r * PQ_EE, n, ldc, pk, p, g, c0, acc, ld_acc,
                                        acc_col0, cur, r0, r1);
     } else {
 #pragma unroll 1
       for (int r = 0; r < PQ_R; ++r)
-        quad_round<NC, LPR, false, VEC>(words, tab, gbase + (int64_t)r * PQ_E, n, ldc, pk, p, g, c0, acc, ld_acc,
+        quad_round<NC, LPR, false, VEC>(words, tab, gbase + (int64_t)r * PQ_EE, n, ldc, pk, p, g, c0, acc, ld_acc,
                                         acc_col0, cur, r0, r1);
     }
     // merge the open runs of adjacent row groups (same p): inclusive segmented scan over the groups
@@ -893,6 +902,7 @@ static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers&
     break;
     switch (nc) {
       PQ_CASE(1) PQ_CASE(2) PQ_CASE(3) PQ_CASE(4) PQ_CASE(5) PQ_CASE(6) PQ_CASE(7) PQ_CASE(8)
+      PQ_CASE(9) PQ_CASE(10) PQ_CASE(11) PQ_CASE(12)
       default: LFE_THROW(LFE_ERR_ARG, "launch_proj: nc=%d", nc);
     }
 #undef PQ_CASE
@@ -1092,6 +1102,7 @@ static void launch_s0_fused(lfe_ctx* h, int nc, const int32_t* const* codes, con
     break;
   switch (nc) {
     S0_CASE(1) S0_CASE(2) S0_CASE(3) S0_CASE(4) S0_CASE(5) S0_CASE(6) S0_CASE(7) S0_CASE(8)
+    S0_CASE(9) S0_CASE(10) S0_CASE(11) S0_CASE(12)
     default: LFE_THROW(LFE_ERR_ARG, "launch_s0_fused: nc=%d", nc);
   }
 #undef S0_CASE
@@ -1424,8 +1435,11 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
     }
     // S0 (weighted sums of every column), column batches of <= PJ_MAXNC; with several FEs one fused pass
     // per batch fills every FE's table, so the columns are read once
-    for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
-      int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+    // (the fused pass of F >= 2 takes S0_MAXNC = 12 columns at once: one bulk reduce of the whole row per big-table
+    // row instead of one per batch -- c5, C = 11: 56 -> 40 ms on one GPU)
+    const int s0_batch = (!plan->det && F >= 2) ? S0_MAXNC : PJ_MAXNC;
+    for (int c0 = 0; c0 < C; c0 += s0_batch) {
+      int nc = C - c0 < s0_batch ? C - c0 : s0_batch;
       ColPtrs cp;
       for (int c = 0; c < nc; ++c) cp.col[c] = in[c0 + c];
       if (plan->det) {
@@ -1515,8 +1529,11 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
     // a very small FE is projected over the big FE's entry list with thread-private bins (k_proj_tiny)
     const int big = plan->big;
     const bool tiny = !plan->det && j != big && n >= 65536 && S.G * (C < PJ_MAXNC ? C : PJ_MAXNC) <= PT_MAX_BINS;
-    for (int c0 = 0; c0 < C; c0 += PJ_MAXNC) {
-      int nc = C - c0 < PJ_MAXNC ? C - c0 : PJ_MAXNC;
+    // the row-group kernel (packed list, other table in L2 / HBM) takes up to 12 columns in one pass
+    const bool quad = !plan->det && !tiny && S.packed && o.n == 1 && o.stage_rows[0] == 0 && n >= 4096 && C <= S0_MAXNC;
+    const int bw = quad ? S0_MAXNC : PJ_MAXNC;
+    for (int c0 = 0; c0 < C; c0 += bw) {
+      int nc = C - c0 < bw ? C - c0 : bw;
       if (plan->det) {
         o.stage_rows[0] = 0;   // (no staging: plain gathers)
         if (weighted) launch_det_proj<true>(h, nc, S, o, Cp, c0, S.acc, Cp, c0, s);

@@ -5,6 +5,7 @@
 constexpr int PJ_T = 256;
 constexpr int PJ_I = 4;  // consecutive entries per thread
 constexpr int PJ_MAXNC = 8;
+constexpr int S0_MAXNC = 12;   // the fused S0 pass takes up to 12 columns at once (c5: C = 11 in ONE pass over the rows)
 
 struct ProjOthers {
   const int32_t* code[LFE_MAX_FE];
@@ -30,7 +31,7 @@ __device__ __forceinline__ void stage_tables(const ProjOthers& oth, int ldc, dou
   __syncthreads();
 }
 struct ColPtrs {
-  const double* col[PJ_MAXNC];
+  const double* col[S0_MAXNC];
 };
 struct MutColPtrs {
   double* col[PJ_MAXNC];         // destination

@@ -701,3 +701,32 @@ def test_demean_l2_blocked_entry_lists_match_oracle(eng, Gs, C, weighted):
         eng.set_option(capi.OPT_L2_BLOCK_BYTES, 48 << 20)
     for a, b in zip(got, exp):
         np.testing.assert_allclose(a.cpu().numpy(), b, rtol=0, atol=2e-12)
+
+
+def test_hard_limits_at_the_edge(eng):
+    """Documented limits of the C ABI are enforced at the edge, not one past it: lfe_solve_spd solves p = 512 and
+    rejects 513; row counts must stay below 2^31 - 1 (codes and permutations are 32-bit)."""
+    import ctypes as C
+    from leanfe_b200 import _capi as capi
+    from leanfe_b200._capi import LfeError
+    rng = np.random.default_rng(512)
+    p = 512
+    M = rng.normal(size=(3 * p, p))
+    A, b = M.T @ M + 1e-3 * np.eye(p), rng.normal(size=p)
+    beta, Ainv, fb = eng.solve_spd(dev(A), dev(b))
+    assert not fb
+    np.testing.assert_allclose(beta.cpu().numpy(), np.linalg.solve(A, b), rtol=1e-7)
+    np.testing.assert_allclose(Ainv.cpu().numpy() @ A, np.eye(p), atol=1e-8)
+    with pytest.raises(LfeError, match="out of range"):
+        eng.solve_spd(dev(np.eye(513)), dev(np.ones(513)))
+    # n = 2^31 - 1 rows: refused before any memory is touched (the pointers are never dereferenced)
+    tiny = torch.zeros(8, dtype=torch.int64, device="cuda")
+    G = C.c_int64(0)
+    rc = eng.lib.lfe_factorize(eng.h, C.c_void_p(tiny.data_ptr()), capi.LFE_I64, (1 << 31) - 1, 0,
+                               C.c_void_p(tiny.data_ptr()), C.byref(G), None, 0, eng.stream)
+    assert rc == -1 and b"n out of range" in eng.lib.lfe_last_error()
+    it, mm, cv = C.c_int(0), C.c_double(0), C.c_int(0)
+    rc = eng.lib.lfe_demean(eng.h, capi.ptr_array([tiny.data_ptr()]), 1, capi.ptr_array([tiny.data_ptr()]),
+                            capi.i64_array([4]), capi.i32_array([0]), 1, 1 << 31, None, 1e-6, 5, 3, -1, 0,
+                            C.byref(it), C.byref(mm), C.byref(cv), eng.stream)
+    assert rc == -1 and b"out of range" in eng.lib.lfe_last_error()
