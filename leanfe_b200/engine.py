@@ -77,7 +77,9 @@ class Engine:
             except Exception:
                 cores = os.cpu_count() or 4
             ranks = max(torch.cuda.device_count() if self.world > 1 else 1, 1)
-            threads = int(os.environ.get("LFE_UPLOAD_THREADS", max(2, min(8, cores // (2 * ranks) or 1))))
+            # staging has to keep up with PCIe (55 GB/s): ~7 GB/s per thread -> up to 12 threads, leaving cores for
+            # the caller and the dispatcher; one rank per GPU shares the host
+            threads = int(os.environ.get("LFE_UPLOAD_THREADS", max(2, min(12, (cores * 3) // (4 * ranks) or 1))))
             u = C.c_void_p()
             capi.check(self.lib.lfe_uploader_create(self.h, 32 << 20, 8, threads, C.byref(u)))
             self._uploader = u
