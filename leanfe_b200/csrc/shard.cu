@@ -138,15 +138,18 @@ struct PushSpec {
   long long row0[P2P_MAX_WORLD];        // first row of MY block inside rank d's column
   int world;
 };
+// CTA b serves destination (b + me) mod world: every sender feeds ALL its peers at once and no destination is the
+// target of all senders at the same moment (a plain grid-stride walk of the send order has every rank writing to
+// rank 0 first, then to rank 1, ... -- eight senders sharing one ingress port)
 template <typename T>
 __global__ void __launch_bounds__(256) k_push_by(const T* __restrict__ src, const uint32_t* __restrict__ order, int64_t n,
-                                                 PushSpec sp) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int d = 0;
-#pragma unroll 1
-    while (d + 1 < sp.world && i >= sp.soff[d + 1]) ++d;
-    reinterpret_cast<T*>(sp.col[d])[sp.row0[d] + (i - sp.soff[d])] = __ldg(src + __ldcs(order + i));
-  }
+                                                 PushSpec sp, int me) {
+  const int d = (int)((blockIdx.x + me) % sp.world);
+  const int64_t lb = blockIdx.x / sp.world, nb = gridDim.x / sp.world;   // gridDim.x is a multiple of world
+  const int64_t lo = sp.soff[d], hi = sp.soff[d + 1];
+  T* __restrict__ dst = reinterpret_cast<T*>(sp.col[d]) + sp.row0[d];
+  for (int64_t i = lo + lb * blockDim.x + threadIdx.x; i < hi; i += nb * blockDim.x)
+    dst[i - lo] = __ldg(src + __ldcs(order + i));
 }
 
 struct P2PInfo {                        // what every rank publishes before an exchange
@@ -216,7 +219,7 @@ static bool exchange_p2p(lfe_ctx* h, const int32_t* order, const int64_t* send_c
   }
   tr.mark("exchange: publish arenas");
   // (2) push every column straight into its owner's arena
-  const int blocks = launch_blocks(h, ceil_div64(n, 256 * 8), 16);
+  const int blocks = ((launch_blocks(h, ceil_div64(n, 256 * 4), 16) + world - 1) / world) * world;   // multiple of world
   std::vector<int64_t> peer_off(world, 0);     // running column offset inside each peer's arena
   for (int c = 0; c < K; ++c) {
     const size_t es = dtype_size(dtypes[c]);
@@ -233,9 +236,9 @@ static bool exchange_p2p(lfe_ctx* h, const int32_t* order, const int64_t* send_c
     sp.soff[world] = acc_rows;
     if (n > 0) {
       const uint32_t* ord = (const uint32_t*)order;
-      if (es == 8) k_push_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, sp);
-      else if (es == 4) k_push_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, sp);
-      else k_push_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, sp);
+      if (es == 8) k_push_by<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)cols_in[c], ord, n, sp, me);
+      else if (es == 4) k_push_by<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)cols_in[c], ord, n, sp, me);
+      else k_push_by<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)cols_in[c], ord, n, sp, me);
       KERNEL_CHECK();
       h->n_launches += 1;
     }
