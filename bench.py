@@ -549,36 +549,57 @@ def main():
                 "coefs": {k_: float(v) for k_, v in list(r.coefs.items())[:10]},
                 "std_errors": {k_: float(v) for k_, v in list(r.std_errors.items())[:10]}}
 
-    c5 = c3 = c4 = None
-    if not args.no_c5:
+    def guarded(fn):
+        """A side record must never cost the headline line: a failure (e.g. out of memory on a smaller part) is
+        reported in the record instead.  Every rank takes the same branch (the failure flag is all-reduced)."""
+        rec, err = None, None
+        try:
+            rec = fn()
+        except Exception as e:       # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"[:300]
+            eng.set_profiling(False)
+        if world > 1:
+            bad_ = torch.tensor([1.0 if err else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(bad_)
+            if bad_.item() > 0 and err is None:
+                err = "failed on another rank"
         torch.cuda.empty_cache()
+        return {"unavailable": err} if err else rec
+
+    def run_c5():
         n5 = args.c5_rows
         shard5 = make_c5_rows(torch, dev, n5 * rank // world, n5 * (rank + 1) // world, n5)
-        c5 = strong_record(f"c5: {n5 // 1_000_000}M rows TOTAL, 10 regressors | unit({n5 // C5_ROWS_PER_UNIT}) + time(500), iid",
-                           shard5, dict(formula=C5_FORMULA, vcov="iid", strategy="alt_proj"), n5)
-        del shard5
-        torch.cuda.empty_cache()
-    if not args.no_extra:
+        return strong_record(f"c5: {n5 // 1_000_000}M rows TOTAL, 10 regressors | unit({n5 // C5_ROWS_PER_UNIT}) + time(500), iid",
+                             shard5, dict(formula=C5_FORMULA, vcov="iid", strategy="alt_proj"), n5)
+
+    def run_c3():
         n3 = args.c3_rows
         shard3 = make_c3_rows(torch, dev, n3 * rank // world, n3 * (rank + 1) // world, n3)
-        c3 = strong_record(f"c3: AKM {n3 // 1_000_000}M rows TOTAL, 2 regressors | worker({n3 // 10}) + firm({n3 // 100}) + "
-                           "year(30), HC1, 50 sweeps", shard3,
-                           dict(formula="y ~ x1 + x2 | worker + firm + year", vcov="hc1", strategy="alt_proj"), n3)
+        rec = strong_record(f"c3: AKM {n3 // 1_000_000}M rows TOTAL, 2 regressors | worker({n3 // 10}) + firm({n3 // 100}) + "
+                            "year(30), HC1, 50 sweeps", shard3,
+                            dict(formula="y ~ x1 + x2 | worker + firm + year", vcov="hc1", strategy="alt_proj"), n3)
         # in-place-equivalent sweep rate (SURVEY 8d: N F (16 C + 8) bytes per sweep of the reference's formulation)
-        sw_ms = (c3["phases_ms_per_fit"].get("demean_sweeps", 0) + c3["phases_ms_per_fit"].get("demean_check", 0)) / max(c3["sweeps"], 1)
+        sw_ms = (rec["phases_ms_per_fit"].get("demean_sweeps", 0) + rec["phases_ms_per_fit"].get("demean_check", 0)) / max(rec["sweeps"], 1)
         if sw_ms > 0:
-            c3["sweep_ms"] = sw_ms
-            c3["sweep_inplace_equivalent_gbs_all_gpus"] = n3 * 3 * (16 * 3 + 8) / (sw_ms / 1e3) / 1e9
-        del shard3
-        torch.cuda.empty_cache()
+            rec["sweep_ms"] = sw_ms
+            rec["sweep_inplace_equivalent_gbs_all_gpus"] = n3 * 3 * (16 * 3 + 8) / (sw_ms / 1e3) / 1e9
+        return rec
+
+    def run_c4():
         n4 = args.c4_rows
         shard4, dnames = make_c4_rows(torch, dev, n4 * rank // world, n4 * (rank + 1) // world)
-        c4 = strong_record(f"c4: YOCO {n4 // 1_000_000}M rows TOTAL, 23 treatment x period dummies | group(1000) + period(24), "
-                           "cluster(group)", shard4,
-                           dict(formula="y ~ " + " + ".join(dnames) + " | group + period", vcov="cluster",
-                                cluster_cols=["group"], strategy="compress"), n4, steps_s=3)
-        del shard4
-        torch.cuda.empty_cache()
+        return strong_record(f"c4: YOCO {n4 // 1_000_000}M rows TOTAL, 23 treatment x period dummies | group(1000) + period(24), "
+                             "cluster(group)", shard4,
+                             dict(formula="y ~ " + " + ".join(dnames) + " | group + period", vcov="cluster",
+                                  cluster_cols=["group"], strategy="compress"), n4, steps_s=3)
+
+    c5 = c3 = c4 = None
+    torch.cuda.empty_cache()
+    if not args.no_c5:
+        c5 = guarded(run_c5)
+    if not args.no_extra:
+        c3 = guarded(run_c3)
+        c4 = guarded(run_c4)
 
     if rank != 0:
         if world > 1:

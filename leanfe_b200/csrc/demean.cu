@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(PT_T, 1) k_proj_tiny(const int32_t* __restrict
   extern __shared__ double priv[];   // [Gj * NC][PT_T]
   const int nbins = Gj * NC;
   for (int i = 0; i < nbins; ++i) priv[i * PT_T + threadIdx.x] = 0.0;   // thread-private: no barrier needed
-  const bool vec2 = ((NC & 1) == 0) && ((ldc & 1) == 0) && ((col0 & 1) == 0);
+  // 128-bit gathers: even NC, or an odd NC whose batch ends at the zero pad column of an even-width table
+  const bool vec2 = ((ldc & 1) == 0) && ((col0 & 1) == 0) && (((NC & 1) == 0) || col0 + NC + 1 <= ldc);
   const int64_t nchunk = ceil_div64(n, (int64_t)PT_T * E);
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
     const int64_t base = (ch * PT_T + threadIdx.x) * E;
@@ -429,10 +430,10 @@ __global__ void __launch_bounds__(PT_T, 1) k_proj_tiny(const int32_t* __restrict
       const double* row = tab_b + (size_t)(kb[e] >= 0 ? kb[e] : 0) * ldc + col0;
       if (vec2) {
 #pragma unroll
-        for (int c = 0; c < NC / 2; ++c) {
+        for (int c = 0; c < (NC + 1) / 2; ++c) {
           const double2 t = *(reinterpret_cast<const double2*>(row) + c);
           v[e][2 * c] = t.x;
-          v[e][2 * c + 1] = t.y;
+          if (2 * c + 1 < NC) v[e][2 * c + 1] = t.y;
         }
       } else {
 #pragma unroll
@@ -447,8 +448,17 @@ __global__ void __launch_bounds__(PT_T, 1) k_proj_tiny(const int32_t* __restrict
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const double* row = tab + (size_t)(oc[e] >= 0 ? oc[e] : 0) * ldc;
+        if (vec2) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[e][c] += row[c];
+          for (int c = 0; c < (NC + 1) / 2; ++c) {
+            const double2 t = *(reinterpret_cast<const double2*>(row) + c);
+            v[e][2 * c] += t.x;
+            if (2 * c + 1 < NC) v[e][2 * c + 1] += t.y;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) v[e][c] += row[c];
+        }
       }
     }
 #pragma unroll
@@ -1402,7 +1412,8 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
   // (128-bit gathers, TMA bulk reduces); the pad column stays zero throughout.  Narrow tables are left alone:
   // padding 3 -> 4 columns makes c3's 240 MB worker table 320 MB and its random gathers 20 % slower (L2 hit
   // rate), and 1 -> 2 would double every table of the per-column runs.
-  const int Cp = (C >= 5 && (C & 1)) ? C + 1 : C;
+  static const bool pad_narrow = getenv("LFE_PAD_NARROW") != nullptr;   // experiment: 3 -> 4 columns as well
+  const int Cp = ((C >= 5 || (pad_narrow && C >= 3)) && (C & 1)) ? C + 1 : C;
   LFE_REQUIRE(max_iter >= 1, "lfe_demean: max_iter must be >= 1");
   {
     bool seen[LFE_MAX_FE] = {false};
@@ -1541,10 +1552,12 @@ static void demean_plan_run_tail(lfe_ctx* h, lfe_plan* plan, double* const* cols
       } else if (tiny) {
         if (weighted) launch_proj_tiny<true>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
         else launch_proj_tiny<false>(h, nc, st, big, j, F, n, Cp, c0, S.acc, Cp, c0, s);
-      } else if (weighted) {
-        launch_proj<true>(h, nc, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
       } else {
-        launch_proj<false>(h, nc, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
+        // an odd batch that ends at the zero pad column takes the pad along: NC even => 128-bit table gathers
+        // (the pad column of S0 / acc / alpha is zero and stays zero)
+        const int ncl = ((nc & 1) && c0 + nc == C && Cp > C && nc + 1 <= bw && (c0 & 1) == 0) ? nc + 1 : nc;
+        if (weighted) launch_proj<true>(h, ncl, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
+        else launch_proj<false>(h, ncl, S, o, n, Cp, c0, S.acc, Cp, c0, proj_smem, s);
       }
     }
     if (dist && j != local_fe) {
