@@ -633,14 +633,16 @@ def main():
     inplace_bytes = n * F * (16 * C + 8)                    # the reference's in-place formulation
     traffic, traffic_src = ncu_traffic("c2_50M_sweep") if (n == 50_000_000 and world == 1) else (None, None)
     roofline = {
-        "bound": "hbm", "kernel": "k_proj_q<6> (time FE) + k_proj<6> (unit FE) + k_finalize (one sweep = 2 projections)",
+        "bound": "hbm", "kernel": "k_proj_q<6,1> (time FE, unit table gathered from L2) + k_proj_rep<6,8> (unit FE, replicated period table "
+                                  "in shared memory) + k_finalize (one sweep = 2 projections)",
         "achieved": own_bytes / (sweep_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": own_bytes / (sweep_ms / 1e3) / 1e9 / peak,
         "traffic": traffic, "traffic_source": traffic_src,
         "basis": "achieved/frac = bytes this implementation's sweep must move (packed code words + tables) / time; "
                  "inplace_equivalent = SURVEY 8(d) bytes of the reference's in-place sweep / the same time",
-        "limiter": "not HBM: shared-memory / L1TEX wavefront pipes of the table gathers (see profiles/); the sweep "
-                   "reads only the packed code words",
+        "limiter": "not HBM: the L1TEX data pipe (l1tex__data_pipe_lsu_wavefronts 76-79 % of peak in "
+                   "profiles/r2_ncu_c2_kernels.md) -- table-row gathers from L2 / shared memory; the sweep reads only the "
+                   "packed code words",
         "peak_source": peak_src, "bytes_per_sweep": own_bytes, "sweep_ms": sweep_ms, "sweeps_per_fit": sweeps,
         "proj_launches_per_fit": proj_launches,
         "inplace_equivalent": {"bytes_per_sweep": inplace_bytes, "achieved": inplace_bytes / (sweep_ms / 1e3) / 1e9,
