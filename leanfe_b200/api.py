@@ -111,9 +111,6 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
     if deterministic:
         if eng.world > 1:
             raise NotImplementedError("deterministic=True is single-GPU only")
-        if strategy in ("auto", "compress"):
-            raise NotImplementedError("deterministic=True covers the FWL strategies: pass strategy='alt_proj', "
-                                      "'demean' or 'ols' (the YOCO group-by sums with atomics)")
     eng.set_option(capi.OPT_DETERMINISTIC, 1 if deterministic else 0)
     if profile:
         eng.set_profiling(True)

@@ -316,6 +316,35 @@ struct Stage {
   int64_t G = 0;
 };
 
+// deterministic mode: stats[q * G + g] = sum over the rows of group g, in row order, of (w | w y | w y^2): one warp per
+// group walks its rows of the group-sorted permutation, fixed shuffle tree, plain stores (no floating-point atomics)
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_det_group_stats(const uint32_t* __restrict__ off, int64_t G,
+                                                         const uint32_t* __restrict__ perm, const double* __restrict__ y,
+                                                         const double* __restrict__ w, double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < G; g += nwarp) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const uint32_t e1 = off[g + 1];
+    for (uint32_t e = off[g] + lane; e < e1; e += 32) {
+      const size_t row = perm[e];
+      const double yv = y[row];
+      if (WEIGHTED) {
+        const double wv = w[row];
+        s0 += wv; s1 += wv * yv; s2 += wv * yv * yv;
+      } else {
+        s1 += yv; s2 += yv * yv;
+      }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+      if (WEIGHTED) { stats[g] = s0; stats[(size_t)G + g] = s1; stats[2 * (size_t)G + g] = s2; }
+      else { stats[g] = s1; stats[(size_t)G + g] = s2; }
+    }
+  }
+}
+
 static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* key_dtypes, const int64_t* n_groups, int K,
                           const double* y,
                           const double* weights, const MergeIn* merge, int64_t n, int64_t out_cap,
@@ -487,7 +516,18 @@ static void compress_core(lfe_ctx* h, const void* const* key_codes, const int* k
     const int win = (int)(((size_t)h->smem_optin - 1024) / (NS * sizeof(double)));
     const int64_t npass = win > 0 ? ceil_div64(G, win) : 1 << 30;
     const bool aligned = vc && (((uintptr_t)y) & 15) == 0 && (!weights || (((uintptr_t)weights) & 15) == 0);
-    if (G > 4096 && npass <= 4 && n >= 64 * G && aligned) {
+    if (h->opt_deterministic) {
+      DevBuf<uint32_t> perm(n, s), off((size_t)G + 1, s);
+      off.zero();
+      prim_histogram(h, gcode, n, G, off, s);
+      prim_exclusive_scan_u32(h, off, off, G + 1, nullptr, s);
+      prim_argsort_u32(h, (const uint32_t*)gcode.p, n, bits_for((uint64_t)(G > 0 ? G - 1 : 0)), perm, nullptr, s);
+      const int db = launch_blocks(h, ceil_div64(G, 8), 8);
+      if (weights) k_det_group_stats<true><<<db, 256, 0, s>>>(off, G, perm, y, weights, stats);
+      else k_det_group_stats<false><<<db, 256, 0, s>>>(off, G, perm, y, nullptr, stats);
+      KERNEL_CHECK();
+      h->n_launches += 1;
+    } else if (G > 4096 && npass <= 4 && n >= 64 * G && aligned) {
       const int B = (int)ceil_div64(G, npass);
       const size_t smem = (size_t)NS * B * sizeof(double);
       static bool attr_set = false;

@@ -820,6 +820,17 @@ __global__ void __launch_bounds__(256) k_yoco_rows(const double* __restrict__ yt
     local += rg;
   }
   local = warp_sum(local);
+  if (gridDim.x == 1) {   // deterministic mode launches ONE block: the warps' partials are added in warp order
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += sh[q];
+      *rss_total += t;
+    }
+    return;
+  }
   if ((threadIdx.x & 31) == 0) atomicAdd(rss_total, local);
 }
 
@@ -839,7 +850,7 @@ void yoco_vcov_impl(lfe_ctx* h, const double* const* cols, int k, int64_t G, con
   DevBuf<double> rss_g(G, s), e0_g(G, s), rss_loc(1, s);
   double* rss = rss_out ? rss_out : rss_loc.p;
   CUDA_CHECK(cudaMemsetAsync(rss, 0, sizeof(double), s));
-  k_yoco_rows<<<launch_blocks(h, ceil_div64(G, 256), 4), 256, 0, s>>>(cols[0], X, k, beta, nn, sum_y, sum_y_sq, G, rss_g,
+  k_yoco_rows<<<h->opt_deterministic ? 1 : launch_blocks(h, ceil_div64(G, 256), 4), 256, 0, s>>>(cols[0], X, k, beta, nn, sum_y, sum_y_sq, G, rss_g,
                                                                       e0_g, rss);
   KERNEL_CHECK();
   h->n_launches += 1;

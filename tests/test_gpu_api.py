@@ -398,5 +398,26 @@ def test_deterministic_mode_is_bit_identical_across_runs(fes, vcov, cl, weighted
     # the default (atomics) path agrees to rounding
     fast = leanfe(dd, **kw)
     np.testing.assert_allclose(list(fast.coefs.values()), list(runs[0].coefs.values()), rtol=1e-11)
-    with pytest.raises(NotImplementedError):
-        leanfe(dd, formula="y ~ x1 | unit + time", strategy="compress", deterministic=True)
+
+
+@pytest.mark.parametrize("vcov,cl,weighted", [("iid", None, False), ("hc1", None, True), ("cluster", ["grp"], False),
+                                              ("cluster", ["grp", "per"], False)])
+def test_deterministic_mode_yoco_is_bit_identical_across_runs(vcov, cl, weighted):
+    from leanfe_b200 import leanfe
+    rng = np.random.default_rng(33)
+    n = 500_000
+    grp, per = rng.integers(0, 300, n), rng.integers(0, 12, n)
+    d = dict(grp=grp, per=per, d1=((grp % 3 == 0) & (per >= 6)).astype(np.uint8), dose=rng.integers(0, 4, n).astype(np.float64),
+             w=rng.integers(1, 4, n).astype(np.float64))
+    d["y"] = 0.8 * d["d1"] + 0.1 * d["dose"] + rng.normal(size=300)[grp] + 0.05 * per + rng.normal(size=n)
+    kw = dict(formula="y ~ d1 + dose | grp + per", strategy="compress", vcov=vcov, cluster_cols=cl,
+              weights="w" if weighted else None)
+    dd = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    runs = [leanfe(dd, deterministic=True, **kw) for _ in range(3)]
+    for r in runs[1:]:
+        assert list(r.coefs.values()) == list(runs[0].coefs.values())
+        assert list(r.std_errors.values()) == list(runs[0].std_errors.values())
+        assert r.rss == runs[0].rss and r.n_compressed == runs[0].n_compressed
+    ref = O.leanfe_oracle(d, **kw)
+    np.testing.assert_allclose(list(runs[0].coefs.values()), list(ref["coefs"].values()), rtol=RTOL_BETA)
+    np.testing.assert_allclose(list(runs[0].std_errors.values()), list(ref["std_errors"].values()), rtol=RTOL_SE)
