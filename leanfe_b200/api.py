@@ -325,6 +325,8 @@ def leanfe_b200(data, demean_tol=1e-6, y_col=None, x_cols=None, fe_cols=None, fo
         return res
     finally:
         up.close()      # every staged host->device copy has completed before the caller's arrays may go away
+        if deterministic:
+            eng.set_option(capi.OPT_DETERMINISTIC, 0)      # the engine is shared: leave it as it was found
 
 
 # ------------------------------------------------------------------------------------------------
