@@ -417,7 +417,8 @@ def main():
         dist.all_reduce(bad)
         mg_parity = {"ok": int(bad.item()) == 0, "world": world, "failed_cases_over_ranks": int(bad.item()),
                      "cases": "two-way iid/hc1/cluster(unit)/cluster(time) pre-partitioned + arbitrary shards "
-                              "(library repartition); three-way weighted / hc1 / cluster(firm) both ways; YOCO x5",
+                              "(library repartition); one-way 'demean' from arbitrary shards; three-way weighted / hc1 / "
+                              "cluster(firm) both ways; YOCO x5",
                      "tolerance": "beta 1e-8, se 1e-6, iterations / n_obs / df_resid / fe_dims / n_clusters equal, "
                                   "results bit-identical on all ranks", "seconds": round(time.perf_counter() - t0, 1)}
         if fails and rank == 0:

@@ -82,6 +82,19 @@ def run_checks(rank: int, world: int) -> list:
         if not ok:
             failures.append(("arbitrary-shards", vc, cl, b, eb, s, es, res.iterations, ref["iterations"], res.n_obs,
                              ref["n_obs"], res.fe_dims, ref["fe_dims"], res.n_clusters, ref["n_clusters"]))
+    # single FE ('demean': the within transform), arbitrary shards: the library repartitions by that FE
+    for vc, cl in (("iid", None), ("cluster", ["unit"])):
+        kw = dict(formula="y ~ x1 + x2 | unit", vcov=vc, cluster_cols=cl, strategy="demean")
+        res = leanfe(shard_a, **kw)
+        ref = O.leanfe_oracle(full, **kw)
+        b, eb = np.array(list(res.coefs.values())), np.array(list(ref["coefs"].values()))
+        s, es = np.array(list(res.std_errors.values())), np.array(list(ref["std_errors"].values()))
+        ok = (np.max(np.abs(b - eb) / np.abs(eb)) < 1e-8 and np.max(np.abs(s - es) / es) < 1e-6
+              and res.n_obs == ref["n_obs"] and res.df_resid == ref["df_resid"]
+              and tuple(res.fe_dims) == tuple(ref["fe_dims"]) and res.n_clusters == ref["n_clusters"])
+        if not ok:
+            failures.append(("demean-arbitrary-shards", vc, cl, b, eb, s, es, res.n_obs, ref["n_obs"], res.df_resid,
+                             ref["df_resid"], res.fe_dims, ref["fe_dims"]))
     # three-way FE (worker = shard key, firm and year shared by all ranks), weighted, max_iter reached
     nw, nf = 9000, 700
     worker = rng.integers(0, nw, N)
