@@ -314,9 +314,9 @@ def cpu_reference_run(d: dict, steps: int, warmup: int):
                 times.append(time.perf_counter() - t0)
         names = [f"x{j}" for j in range(1, K_REG + 1)]
         return dict(rate=n * len(times) / sum(times), cores=host_cores(), kind="reference", note=why,
-                    sec=float(np.mean(times)), beta=np.array([res["coefficients"][c] for c in names]),
-                    se=np.array([res["std_errors"][c] for c in names]), iterations=int(res["iterations"]),
-                    n_obs=int(res["n_obs"]))
+                    sec=float(np.mean(times)), beta=np.array([res.coefs[c] for c in names]),
+                    se=np.array([res.std_errors[c] for c in names]), iterations=int(res.iterations),
+                    n_obs=int(res.n_obs))
     from oracle import ref_port as P
     cores = P.set_threads(host_cores())      # torchrun exports OMP_NUM_THREADS=1 to its workers: set it explicitly
     res = None

@@ -453,6 +453,6 @@ def test_live_reference_when_polars_is_present():
         ref = ref_leanfe(pl.DataFrame(d), backend="polars", **kw)
         res = leanfe(d, **kw)
         for name in ("x1", "x2"):
-            assert abs(res.coefs[name] - ref["coefficients"][name]) / abs(ref["coefficients"][name]) < RTOL_BETA
-            assert abs(res.std_errors[name] - ref["std_errors"][name]) / ref["std_errors"][name] < RTOL_SE
-        assert res.iterations == ref["iterations"] and res.n_obs == ref["n_obs"]
+            assert abs(res.coefs[name] - ref.coefs[name]) / abs(ref.coefs[name]) < RTOL_BETA
+            assert abs(res.std_errors[name] - ref.std_errors[name]) / ref.std_errors[name] < RTOL_SE
+        assert res.iterations == ref.iterations and res.n_obs == ref.n_obs
