@@ -130,3 +130,34 @@ def test_argument_errors_follow_reference():
     with pytest.raises(ValueError, match="Unknown strategy"):
         leanfe(d, formula="y ~ x", strategy="magic")
     assert issubclass(InvalidVcov, AssertionError)
+
+
+def test_bench_live_reference_branch_with_a_stand_in(monkeypatch):
+    """bench.cpu_reference_run takes the real reference when `import polars` works (it cannot on this image): drive
+    that branch with stand-ins for polars and for leanfe() so that it cannot rot unexecuted."""
+    import sys
+    import types
+
+    import numpy as np
+
+    import bench
+
+    calls = {}
+
+    class FakeRes:
+        coefs = {f"x{j}": 1.0 + 0.1 * j for j in range(1, 6)}
+        std_errors = {f"x{j}": 0.01 * j for j in range(1, 6)}
+        iterations, n_obs = 4, 1000
+
+    def fake_leanfe(df, **kw):
+        calls.update(kw, rows=len(df["y"]))
+        return FakeRes()
+
+    monkeypatch.setitem(sys.modules, "polars", types.SimpleNamespace(DataFrame=lambda d: d))
+    monkeypatch.setattr(bench, "live_reference", lambda: (fake_leanfe, "polars importable"))
+    d, _ = bench.make_panel(1000, 1)
+    r = bench.cpu_reference_run(d, steps=2, warmup=1)
+    assert r["kind"] == "reference" and r["iterations"] == 4 and r["n_obs"] == 1000 and r["rate"] > 0
+    np.testing.assert_allclose(r["beta"], [1.1, 1.2, 1.3, 1.4, 1.5])
+    assert calls["backend"] == "polars" and calls["strategy"] == "alt_proj" and calls["cluster_cols"] == ["unit"]
+    assert calls["rows"] == 1000
