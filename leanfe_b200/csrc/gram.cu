@@ -213,7 +213,7 @@ void gram_impl(lfe_ctx* h, const double* const* cols, int C, int64_t n, const do
 // k_gram_tri (read N x C): N*(8C + 4F) bytes instead of N*(24C + 4F).
 // ---------------------------------------------------------------------------------------------
 template <int NC, int R, bool VEC, bool WEIGHTED>
-__global__ void __launch_bounds__(TL_T) k_tail_gram(TailCols cols, TailTabs T, const double* __restrict__ w, int64_t n,
+__global__ void __launch_bounds__(TL_T, (NC <= 6 ? 2 : 1)) k_tail_gram(TailCols cols, TailTabs T, const double* __restrict__ w, int64_t n,
                                                     int ldc, double* __restrict__ partials) {
   constexpr int P = NC + 1;
   constexpr int NT = P * (P + 1) / 2;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(TL_T) k_tail_gram(TailCols cols, TailTabs T, c
 template <int NC, bool WEIGHTED>
 static void launch_tail_gram(lfe_ctx* h, const TailCols& cols, const TailTabs& T, const double* w, int64_t n, int ldc,
                              size_t smem, bool vec, double* gram_out, cudaStream_t s) {
-  constexpr int R = TailCfg<NC>::R;
+  constexpr int R = TailCfg<NC>::R_GRAM;
   constexpr int P = NC + 1, NT = P * (P + 1) / 2;
   const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)TL_T * R), NC <= 8 ? 2 : 1);
   DevBuf<double> partials((size_t)blocks * NT, s);
