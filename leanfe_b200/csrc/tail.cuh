@@ -18,7 +18,7 @@ typedef ProjOthers TailTabs;
 // rows per thread: all loads of a thread's rows are issued before the first use, so the gathers of R rows overlap
 template <int NC>
 struct TailCfg {
-  static constexpr int R = NC <= 6 ? 4 : (NC <= 8 ? 2 : 1);        // residual / score pass
+  static constexpr int R = NC <= 4 ? 4 : (NC <= 8 ? 2 : 1);        // residual / score pass (5-8 columns: 3 CTAs per SM)
   // Gram pass: its (NC+1)(NC+2)/2 accumulators come on top, so 5-6 columns take 2 rows per thread and stay within
   // 128 registers = two CTAs per SM (c2: 0.99 -> 0.76 ms; 4 rows per thread needed 176 registers, one CTA per SM)
   static constexpr int R_GRAM = NC <= 4 ? 4 : (NC <= 8 ? 2 : 1);

@@ -624,7 +624,9 @@ void resid_vcov_fused_impl(lfe_ctx* h, const double* const* cols, int C, int64_t
   TailCols tc;
   for (int c = 0; c < C; ++c) tc.col[c] = cols[c];
   const bool vec = tail_aligned(tc, C, T, weights) && (vcov_kind != LFE_VCOV_CLUSTER || ((((uintptr_t)cl) & 15) == 0));
-  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)TL_T * 2), C <= 8 ? 2 : 1);
+  // 5-8 columns: 2 rows per thread, 78 registers -> three CTAs per SM (c2: 1.97 -> 1.74 ms; four thrash the L2 between
+  // the unit table and the score table: 2.36 ms)
+  const int blocks = launch_blocks(h, ceil_div64(n, (int64_t)TL_T * 2), C <= 4 ? 2 : (C <= 8 ? 3 : 1));
   const int ldS = (k >= 5 && (k & 1)) ? k + 1 : k;
   const int ntm = k > 0 ? k * (k + 1) / 2 : 1;
   DevBuf<double> partials((size_t)blocks * 4, s), raw(4, s), stats_local(4, s);
