@@ -154,7 +154,7 @@ __device__ __forceinline__ void proj_batch(const int32_t* __restrict__ key, cons
 }
 
 template <int NC, bool WEIGHTED, bool PACKED>
-__global__ void __launch_bounds__(PJ_T, (NC <= 4 ? 3 : 2)) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
+__global__ void __launch_bounds__(PJ_T, (NC <= 4 ? 4 : 2)) k_proj(const int32_t* __restrict__ key, ProjOthers oth,
                                                const double* __restrict__ w, int64_t n, int ldc, int col0,
                                                double* __restrict__ acc, int ld_acc, int acc_col0, bool vec_codes,
                                                PackSpec pk) {
@@ -892,7 +892,7 @@ template <bool WEIGHTED>
 static void launch_proj(lfe_ctx* h, int nc, const FEState& st, const ProjOthers& oth, int64_t n, int ldc, int col0,
                         double* acc, int ld_acc, int acc_col0, size_t smem, cudaStream_t s) {
   int64_t nchunk = ceil_div64(n, (int64_t)PJ_T * PJ_I * PJ_NB);
-  int blocks = launch_blocks(h, nchunk, nc <= 4 ? 3 : 2);   // persistent: 2-3 CTAs per SM (register-limited), tables staged once
+  int blocks = launch_blocks(h, nchunk, nc <= 4 ? 4 : 2);   // persistent: 2-3 CTAs per SM (register-limited), tables staged once
   bool vec = aligned16(st.key);
   if (!st.packed)
     for (int o = 0; o < oth.n; ++o) vec = vec && aligned16(oth.code[o]);
