@@ -161,3 +161,28 @@ def test_bench_live_reference_branch_with_a_stand_in(monkeypatch):
     np.testing.assert_allclose(r["beta"], [1.1, 1.2, 1.3, 1.4, 1.5])
     assert calls["backend"] == "polars" and calls["strategy"] == "alt_proj" and calls["cluster_cols"] == ["unit"]
     assert calls["rows"] == 1000
+
+
+def test_bench_panels_are_pure_functions_of_the_global_row_index():
+    """The strong-scaling records of bench.py claim 'the same panel at every N': every generator must give bit-identical
+    rows whatever the shard boundaries and chunking (counter-based RNG keyed by the global row index)."""
+    import torch
+
+    import bench
+
+    n_total = 3_000_000
+    whole5 = bench.make_c5_rows(torch, "cpu", 0, 120_000, n_total, chunk=50_000)
+    whole3 = bench.make_c3_rows(torch, "cpu", 0, 120_000, n_total, chunk=70_000)
+    whole4, names4 = bench.make_c4_rows(torch, "cpu", 0, 120_000, chunk=33_333)
+    for lo, hi in ((0, 40_000), (40_000, 120_000), (77_777, 99_999)):
+        for whole, part in ((whole5, bench.make_c5_rows(torch, "cpu", lo, hi, n_total)),
+                            (whole3, bench.make_c3_rows(torch, "cpu", lo, hi, n_total)),
+                            (whole4, bench.make_c4_rows(torch, "cpu", lo, hi)[0])):
+            for k, v in part.items():
+                assert torch.equal(v, whole[k][lo:hi]), k
+    # shapes of the named configs: ids in range, 23 event-study dummies, treated groups only
+    assert int(whole5["unit"].max()) < n_total // bench.C5_ROWS_PER_UNIT and int(whole5["time"].max()) < bench.N_TIME
+    assert int(whole3["worker"].max()) < n_total // 10 and int(whole3["firm"].max()) < n_total // 100
+    assert len(names4) == 23 and "d11" not in names4
+    on = whole4["d12"].bool()
+    assert bool((whole4["group"][on] < 400).all()) and bool((whole4["period"][on] == 12).all())
